@@ -1,0 +1,147 @@
+"""GPU parity of the tcgen05 implicit-GEMM kernel (csrc/igemm.cu) through the C ABI against a
+plain PyTorch fp32 reference of the same op (inputs rounded to fp16 first, fp32 math, TF32 off).
+Tolerance: fp16 output rounding (rtol 1e-3) + fp32 accumulation-order noise (atol scaled by sqrt(K))."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _setup(uav_lib):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+
+
+def _close(got, ref, K, what):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = 1e-3 * ref.abs() + 2e-3 * math.sqrt(K) * 0.02 + 1e-3
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad}/{err.numel()} mismatches, max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 16), (128, 64, 256), (1000, 512, 512), (300, 1024, 1024),
+                                   (2, 256, 1024), (4096, 320, 128), (257, 72, 40), (130, 512, 4)])
+def test_linear(M, K, N):
+    from upscale_a_video_b200 import ops
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    b = torch.randn(N, device="cuda")
+    out = ops.linear(a, w, b)
+    ref = a.float() @ w.float().t() + b
+    _close(out, ref, K, f"linear {M}x{K}x{N}")
+
+
+def test_linear_epilogue_variants():
+    from upscale_a_video_b200 import ops
+    M, K, N = 777, 512, 512
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    b = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").half()
+    rv = torch.randn(3, N, device="cuda").half()
+    out = ops.linear(a, w, b, residual=res, rowvec=rv, rows_per_vec=259, act=ops.ACT_SILU)
+    lin = a.float() @ w.float().t() + b + rv.float()[torch.arange(M, device="cuda") // 259]
+    ref = F.silu(lin) + res.float()
+    _close(out, ref, K, "linear+rowvec+silu+res")
+    out32 = ops.linear(a, w, None, out_dtype=torch.float32)
+    _close(out32, a.float() @ w.float().t(), K, "linear fp32 out")
+    # write into a channel slice of a wider buffer
+    buf = torch.zeros(M, N + 64, device="cuda", dtype=torch.float16)
+    ops.linear(a, w, b, out=buf[:, 64:])
+    _close(buf[:, 64:], a.float() @ w.float().t() + b, K, "linear slice out")
+    assert buf[:, :64].abs().max().item() == 0
+
+
+def test_geglu():
+    from upscale_a_video_b200 import ops
+    M, K, N = 515, 512, 4096
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    b = torch.randn(N, device="cuda") * 0.1
+    out = ops.linear(a, w, b, act=ops.ACT_GEGLU)
+    y = a.float() @ w.float().t() + b
+    h, g = y.chunk(2, dim=-1)
+    _close(out, h * F.gelu(g), K, "geglu")
+
+
+def _conv_ref(x, w, b, stride=1, padding=1):
+    # x (NB,H,W,C) channels-last; w (Cout,k,k,Cin)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b, stride=stride, padding=padding)
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,k", [
+    (2, 16, 16, 64, 64, 3), (3, 40, 72, 128, 256, 3), (2, 33, 47, 64, 128, 3), (1, 64, 64, 8, 256, 3),
+    (2, 24, 40, 256, 4, 3), (2, 20, 36, 768, 256, 3), (2, 20, 36, 192, 64, 1), (1, 8, 8, 512, 512, 3),
+    (1, 128, 160, 64, 32, 3),
+])
+def test_conv2d(NB, H, W, Cin, Cout, k):
+    from upscale_a_video_b200 import ops
+    x = torch.randn(NB, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, k, k, Cin, device="cuda") * 0.05).half()
+    b = torch.randn(Cout, device="cuda")
+    out = ops.conv2d(x, w, b)
+    ref = _conv_ref(x, w, b, 1, k // 2)
+    _close(out, ref, Cin * k * k, f"conv2d {NB}x{H}x{W} {Cin}->{Cout} k{k}")
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,pad_mode", [(2, 32, 48, 64, 64, 0), (3, 40, 72, 256, 256, 0),
+                                                      (1, 18, 22, 128, 128, 0), (2, 32, 48, 128, 128, 1)])
+def test_conv2d_stride2(NB, H, W, Cin, Cout, pad_mode):
+    from upscale_a_video_b200 import ops
+    x = torch.randn(NB, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda") * 0.05).half()
+    b = torch.randn(Cout, device="cuda")
+    out = ops.conv2d(x, w, b, stride=2, pad_mode=pad_mode)
+    if pad_mode == 0:
+        ref = _conv_ref(x, w, b, 2, 1)
+    else:
+        xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+        ref = F.conv2d(xp, w.float().permute(0, 3, 1, 2), b, stride=2).permute(0, 2, 3, 1)
+    _close(out, ref, Cin * 9, f"conv2d s2 pad_mode{pad_mode}")
+
+
+def test_conv2d_slice_in_and_residual_temb():
+    from upscale_a_video_b200 import ops
+    B, T, H, W, C0, C1, Cout = 2, 3, 20, 28, 64, 128, 128
+    buf = torch.randn(B, T, H, W, C0 + C1, device="cuda").half()
+    x = buf[..., C0:]
+    w = (torch.randn(Cout, 3, 3, C1, device="cuda") * 0.05).half()
+    b = torch.randn(Cout, device="cuda")
+    temb = torch.randn(B, Cout, device="cuda").half()
+    res = torch.randn(B, T, H, W, Cout, device="cuda").half()
+    out = ops.conv2d(x, w, b, rowvec=temb, rows_per_vec=T * H * W, residual=res)
+    ref = _conv_ref(x.reshape(B * T, H, W, C1), w, b).reshape(B, T, H, W, Cout)
+    ref = ref + temb.float()[:, None, None, None, :] + res.float()
+    _close(out, ref, C1 * 9, "conv2d slice+temb+res")
+
+
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout,k", [(2, 8, 12, 20, 64, 64, 3), (1, 5, 16, 24, 256, 256, 5),
+                                                (2, 1, 9, 11, 128, 128, 3), (1, 3, 40, 40, 512, 512, 5)])
+def test_conv_temporal(B, T, H, W, Cin, Cout, k):
+    from upscale_a_video_b200 import ops
+    x = torch.randn(B, T, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, k, Cin, device="cuda") * 0.05).half()
+    b = torch.randn(Cout, device="cuda")
+    out = ops.conv_temporal(x, w, b)
+    w5 = w.float().permute(0, 2, 1)[:, :, :, None, None]  # (Cout, Cin, k, 1, 1)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w5, b, padding=(k // 2, 0, 0)).permute(0, 2, 3, 4, 1)
+    _close(out, ref, Cin * k, f"conv_temporal k{k}")
+
+
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout", [(1, 3, 16, 24, 64, 64), (2, 2, 20, 20, 128, 128)])
+def test_conv3d(B, T, H, W, Cin, Cout):
+    from upscale_a_video_b200 import ops
+    x = torch.randn(B, T, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, 3, 3, 3, Cin, device="cuda") * 0.05).half()
+    b = torch.randn(Cout, device="cuda")
+    out = ops.conv3d(x, w, b)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float().permute(0, 4, 1, 2, 3), b, padding=1)
+    _close(out, ref.permute(0, 2, 3, 4, 1), Cin * 27, "conv3d")

@@ -1,0 +1,88 @@
+"""ctypes binding of libuav_b200.so (the C ABI declared in include/uav_b200.h).
+
+There is deliberately NO fallback: if the shared object is missing or a call fails, a
+RuntimeError is raised (SURVEY.md §8b "Errors": non-zero status -> Python raises).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libuav_b200.so"
+_lib = None
+
+
+class UavError(RuntimeError):
+    pass
+
+
+class Epilogue(C.Structure):
+    """uav_epilogue_t"""
+    _fields_ = [
+        ("bias", C.c_void_p),
+        ("rowvec", C.c_void_p),
+        ("rows_per_vec", C.c_int64),
+        ("ld_rowvec", C.c_int64),
+        ("residual", C.c_void_p),
+        ("ld_res", C.c_int64),
+        ("act", C.c_int),
+        ("out_dtype", C.c_int),
+        ("ld_out", C.c_int64),
+    ]
+
+
+I64, I32, P, F32 = C.c_int64, C.c_int, C.c_void_p, C.c_float
+EP = C.POINTER(Epilogue)
+
+# name -> argtypes (restype is int status unless listed in _SPECIAL)
+_PROTOS = {
+    "uav_linear": [P, I64, I64, I64, P, I64, P, EP, P],
+    "uav_conv2d": [P, I64, I64, I64, I64, I64, P, I64, I32, I32, I32, P, EP, P],
+    "uav_conv_temporal": [P, I64, I64, I64, I64, I64, P, I64, I32, P, EP, P],
+    "uav_conv3d": [P, I64, I64, I64, I64, I64, I64, P, I64, P, EP, P],
+}
+_SPECIAL = {
+    "uav_version": (C.c_char_p, []),
+    "uav_last_error_string": (C.c_char_p, []),
+    "uav_launch_count": (C.c_uint64, []),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def declared_symbols():
+    return list(_PROTOS) + list(_SPECIAL)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise UavError(
+            f"{_LIB_PATH} not found: build it with `python -m upscale_a_video_b200.build` "
+            "(nvcc, sm_100a). There is no CPU / PyTorch fallback for the sampling path."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name, (restype, argtypes) in _SPECIAL.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().uav_last_error_string().decode(errors="replace")
+        raise UavError(f"{what} failed (status {status}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().uav_launch_count())

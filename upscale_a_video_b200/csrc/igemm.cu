@@ -1,0 +1,766 @@
+// igemm.cu — the tcgen05 implicit-GEMM kernel behind every convolution and Linear on the
+// Upscale-A-Video sampling path.
+//
+//   out[pixel][n] = epilogue( sum_{tap, c} A[pixel + off(tap)][c] * W[n][tap][c] )
+//
+// Design (B200-first, not a cuDNN translation):
+//  * activations stay channels-last, so an M-tile of 128 output pixels is a rectangular box
+//    of the input tensor and ONE TMA box load per filter tap (shifted coordinates, hardware
+//    zero fill outside the image = the convolution's zero padding) lands directly in the
+//    128B-swizzled K-major layout tcgen05.mma consumes — no im2col buffer, no layout copies
+//    (the reference pays two permute copies per conv: resnet.py:97-99).
+//  * persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA
+//    issuer (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16),
+//    warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/temb/act/residual ->
+//    16B stores).  Two TMEM accumulators so the epilogue of tile i overlaps the main loop of
+//    tile i+1; a STAGES-deep smem ring of {A 128x64, B BLOCK_Nx64} fp16 tiles.
+//  * stride-2 convs read a 5-D "phase" view (2C, W/2, 2, H/2, NB) of the same buffer, the
+//    temporal (k,1,1) conv a (C, HW, T, B) view, Conv3d a (C, W, H, T, B) view, Linear a
+//    (K, M) view: all the same kernel, only the tensor map and the tap table differ.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "uav_common.cuh"
+
+namespace uav {
+
+// ---------------------------------------------------------------------------------------
+// host-side globals shared by all translation units
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+std::atomic<uint64_t> g_launches{0};
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // fp16 elements: one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int MAX_TAPS = 27;
+constexpr int NUM_THREADS = 256;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct alignas(64) IgemmParams {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  int32_t tap_off[MAX_TAPS][5];  // coordinate offset of each tap (dim0 = channel offset)
+  int32_t num_taps;
+  int32_t kblocks_per_tap;
+  int32_t k_per_tap;
+  uint32_t box[5];       // box[0] = 64, box[1..4] = M-tile extents (product 128)
+  uint32_t tiles[5];     // tiles along dims 1..4
+  uint32_t out_dims[5];  // output extents along dims 1..4
+  uint32_t n_tiles, num_tiles;
+  int32_t N;      // rows of B
+  int32_t n_out;  // output columns (N, or N/2 with GEGLU)
+  const float* bias;
+  const __half* rowvec;
+  int64_t rows_per_vec, ld_rowvec;
+  const __half* residual;
+  int64_t ld_res;
+  int32_t act, out_dtype;
+  int64_t ld_out;
+  void* out;
+};
+
+template <int BLOCK_N>
+struct IgemmCfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
+                                   : (2 * BLOCK_N <= 64)  ? 64
+                                   : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256
+                                                          : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BLOCK_N, bool GEGLU>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    igemm_kernel(const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment (SWIZZLE_128B atoms) in the shared address space
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tempty_bar[1], 4);
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.num_taps * p.kblocks_per_tap;
+
+  if (warp_idx == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const uint32_t n_tile = tile % p.n_tiles;
+        uint32_t idx = tile / p.n_tiles;
+        const int c1 = (idx % p.tiles[1]) * p.box[1];
+        idx /= p.tiles[1];
+        const int c2 = (idx % p.tiles[2]) * p.box[2];
+        idx /= p.tiles[2];
+        const int c3 = (idx % p.tiles[3]) * p.box[3];
+        idx /= p.tiles[3];
+        const int c4 = idx * p.box[4];
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int o0 = p.tap_off[tap][0], o1 = p.tap_off[tap][1], o2 = p.tap_off[tap][2],
+                    o3 = p.tap_off[tap][3], o4 = p.tap_off[tap][4];
+          for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_5d(&p.map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES,
+                        kc * BLOCK_K + o0, c1 + o1, c2 + o2, c3 + o3, c4 + o4);
+            const int kcoord = tap * p.k_per_tap + kc * BLOCK_K;
+            uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+            if (GEGLU) {
+              tma_load_2d(&p.map_b, &full_bar[stage], sb, kcoord, n_tile * (BLOCK_N / 2));
+              tma_load_2d(&p.map_b, &full_bar[stage], sb + Cfg::B_STAGE_BYTES / 2, kcoord,
+                          p.N / 2 + n_tile * (BLOCK_N / 2));
+            } else {
+              tma_load_2d(&p.map_b, &full_bar[stage], sb, kcoord, n_tile * BLOCK_N);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(0 /*f16*/, BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the 128B swizzle row: +2 (>>4)
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // =============================== epilogue ===============================
+    const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    const uint32_t row = quad * 32 + lane;
+    uint32_t r = row;
+    const uint32_t l1 = r % p.box[1];
+    r /= p.box[1];
+    const uint32_t l2 = r % p.box[2];
+    r /= p.box[2];
+    const uint32_t l3 = r % p.box[3];
+    r /= p.box[3];
+    const uint32_t l4 = r;
+    const bool vec_ok = (p.ld_out % 8 == 0) && (p.n_out % 8 == 0) &&
+                        (p.residual == nullptr || p.ld_res % 8 == 0) &&
+                        (p.rowvec == nullptr || p.ld_rowvec % 8 == 0);
+    constexpr int OUT_TILE_N = GEGLU ? BLOCK_N / 2 : BLOCK_N;
+    constexpr int CHUNK = (OUT_TILE_N >= 32) ? 32 : 16;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const uint32_t n_tile = tile % p.n_tiles;
+      uint32_t idx = tile / p.n_tiles;
+      const uint32_t o1 = (idx % p.tiles[1]) * p.box[1] + l1;
+      idx /= p.tiles[1];
+      const uint32_t o2 = (idx % p.tiles[2]) * p.box[2] + l2;
+      idx /= p.tiles[2];
+      const uint32_t o3 = (idx % p.tiles[3]) * p.box[3] + l3;
+      idx /= p.tiles[3];
+      const uint32_t o4 = idx * p.box[4] + l4;
+      const bool row_ok = o1 < p.out_dims[1] && o2 < p.out_dims[2] && o3 < p.out_dims[3] &&
+                          o4 < p.out_dims[4];
+      const int64_t out_row =
+          ((static_cast<int64_t>(o4) * p.out_dims[3] + o3) * p.out_dims[2] + o2) * p.out_dims[1] +
+          o1;
+      const __half* rv =
+          (p.rowvec != nullptr && row_ok) ? p.rowvec + (out_row / p.rows_per_vec) * p.ld_rowvec
+                                          : nullptr;
+      const __half* res = (p.residual != nullptr && row_ok) ? p.residual + out_row * p.ld_res
+                                                            : nullptr;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+
+#pragma unroll 1
+      for (int c = 0; c < OUT_TILE_N / CHUNK; ++c) {
+        float v[CHUNK];
+        if constexpr (CHUNK == 32) {
+          uint32_t a[32];
+          tmem_ld_32x32(taddr + c * 32, a);
+          if constexpr (GEGLU) {
+            uint32_t g[32];
+            tmem_ld_32x32(taddr + BLOCK_N / 2 + c * 32, g);
+            tmem_ld_wait();
+            const int n0 = n_tile * OUT_TILE_N + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float h = __uint_as_float(a[j]);
+              float gg = __uint_as_float(g[j]);
+              if (p.bias != nullptr) {
+                h += __ldg(p.bias + n0 + j);
+                gg += __ldg(p.bias + p.N / 2 + n0 + j);
+              }
+              v[j] = h * gelu_erf_f(gg);
+            }
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]);
+          }
+        } else {
+          uint32_t a[16];
+          tmem_ld_32x16(taddr + c * 16, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]);
+        }
+        const int n0 = n_tile * OUT_TILE_N + c * CHUNK;
+        if (!row_ok || n0 >= p.n_out) continue;
+        if (vec_ok) {
+          // all 8-column groups are either fully valid or fully out of range
+#pragma unroll
+          for (int g8 = 0; g8 < CHUNK / 8; ++g8) {
+            const int n = n0 + g8 * 8;
+            if (n >= p.n_out) break;
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = v[g8 * 8 + j];
+            if (!GEGLU && p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            if (rv != nullptr) {
+              const uint4 q = ldg16(rv + n);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                x[2 * j] += f.x;
+                x[2 * j + 1] += f.y;
+              }
+            }
+            if (p.act == UAV_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+            }
+            if (res != nullptr) {
+              const uint4 q = ldg16(res + n);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                x[2 * j] += f.x;
+                x[2 * j + 1] += f.y;
+              }
+            }
+            if (p.out_dtype == UAV_F16) {
+              uint4 o;
+              o.x = pack_half2(x[0], x[1]);
+              o.y = pack_half2(x[2], x[3]);
+              o.z = pack_half2(x[4], x[5]);
+              o.w = pack_half2(x[6], x[7]);
+              stg16(reinterpret_cast<__half*>(p.out) + out_row * p.ld_out + n, o);
+            } else {
+              float* op = reinterpret_cast<float*>(p.out) + out_row * p.ld_out + n;
+              *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+          }
+        } else {
+          for (int j = 0; j < CHUNK; ++j) {
+            const int n = n0 + j;
+            if (n >= p.n_out) break;
+            float x = v[j];
+            if (!GEGLU && p.bias != nullptr) x += __ldg(p.bias + n);
+            if (rv != nullptr) x += __half2float(rv[n]);
+            if (p.act == UAV_ACT_SILU) x = silu_f(x);
+            if (res != nullptr) x += __half2float(res[n]);
+            if (p.out_dtype == UAV_F16)
+              reinterpret_cast<__half*>(p.out)[out_row * p.ld_out + n] = __float2half_rn(x);
+            else
+              reinterpret_cast<float*>(p.out)[out_row * p.ld_out + n] = x;
+          }
+        }
+      }
+      // release this accumulator to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host: descriptor + launch
+// ---------------------------------------------------------------------------------------
+struct IgemmDesc {
+  const void* a;
+  int rank_a;                // always encoded as rank 5
+  uint64_t a_dims[5];        // dim0 = channels
+  uint64_t a_strides[5];     // elements; a_strides[0] == 1
+  uint32_t box[5];           // box[0] = 64
+  uint32_t tiles[5];
+  uint32_t out_dims[5];
+  int num_taps;
+  int32_t tap_off[MAX_TAPS][5];
+  int k_per_tap;
+  const void* w;
+  int64_t N;
+  void* out;
+  const uav_epilogue_t* epi;
+};
+
+template <int BLOCK_N, bool GEGLU>
+static uav_status_t launch_instance(IgemmParams& p, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    UAV_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, GEGLU>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const uint32_t grid = p.num_tiles < (uint32_t)num_sms() ? p.num_tiles : (uint32_t)num_sms();
+  igemm_kernel<BLOCK_N, GEGLU><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  UAV_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return UAV_OK;
+}
+
+static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
+  const uav_epilogue_t* e = d.epi;
+  UAV_REQUIRE(e != nullptr, "igemm: epilogue descriptor is NULL");
+  UAV_REQUIRE(d.a && d.w && d.out, "igemm: null pointer");
+  UAV_REQUIRE(d.k_per_tap > 0 && d.k_per_tap % 8 == 0,
+              "igemm: input channels (%d) must be a positive multiple of 8", d.k_per_tap);
+  UAV_REQUIRE((reinterpret_cast<uintptr_t>(d.a) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(d.w) & 15) == 0,
+              "igemm: operands must be 16-byte aligned");
+  const bool geglu = e->act == UAV_ACT_GEGLU;
+  UAV_REQUIRE(!geglu || (d.N % 256 == 0), "igemm: GEGLU needs N %% 256 == 0 (N=%lld)",
+              (long long)d.N);
+  PFN_encodeTiled encode = get_encode_tiled();
+  UAV_REQUIRE(encode != nullptr, "igemm: cuTensorMapEncodeTiled entry point unavailable");
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  int block_n;
+  if (geglu) block_n = 256;
+  else if (d.N > 128) block_n = 256;
+  else if (d.N > 64) block_n = 128;
+  else if (d.N > 32) block_n = 64;
+  else if (d.N > 16) block_n = 32;
+  else block_n = 16;
+
+  // A map
+  {
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; ++i) {
+      dims[i] = d.a_dims[i];
+      box[i] = d.box[i];
+      UAV_REQUIRE(dims[i] >= 1 && box[i] >= 1 && box[i] <= 256, "igemm: bad A dim/box %d", i);
+    }
+    for (int i = 1; i < 5; ++i) {
+      strides[i - 1] = d.a_strides[i] * 2;
+      UAV_REQUIRE(strides[i - 1] % 16 == 0, "igemm: A stride %d not 16-byte aligned", i);
+    }
+    CUresult r = encode(&p.map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d.a),
+                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAV_REQUIRE(r == CUDA_SUCCESS, "igemm: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  // B map: [N][K_total] K-major
+  const int64_t k_total = (int64_t)d.num_taps * d.k_per_tap;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d.N};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(geglu ? block_n / 2 : block_n)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&p.map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d.w), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAV_REQUIRE(r == CUDA_SUCCESS, "igemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  UAV_REQUIRE(d.num_taps >= 1 && d.num_taps <= MAX_TAPS, "igemm: bad tap count %d", d.num_taps);
+  memcpy(p.tap_off, d.tap_off, sizeof(int32_t) * 5 * d.num_taps);
+  p.num_taps = d.num_taps;
+  p.k_per_tap = d.k_per_tap;
+  p.kblocks_per_tap = (d.k_per_tap + BLOCK_K - 1) / BLOCK_K;
+  uint64_t m_tiles = 1;
+  uint32_t box_prod = 1;
+  for (int i = 0; i < 5; ++i) {
+    p.box[i] = d.box[i];
+    p.tiles[i] = d.tiles[i];
+    p.out_dims[i] = d.out_dims[i];
+    if (i >= 1) {
+      m_tiles *= d.tiles[i];
+      box_prod *= d.box[i];
+    }
+  }
+  UAV_REQUIRE(box_prod == BLOCK_M && d.box[0] == 64, "igemm: M-tile box must cover 128 rows");
+  p.N = (int32_t)d.N;
+  p.n_out = (int32_t)(geglu ? d.N / 2 : d.N);
+  const int out_tile_n = geglu ? block_n / 2 : block_n;
+  p.n_tiles = (uint32_t)((p.n_out + out_tile_n - 1) / out_tile_n);
+  UAV_REQUIRE(m_tiles * p.n_tiles < (1ull << 31), "igemm: too many tiles");
+  p.num_tiles = (uint32_t)(m_tiles * p.n_tiles);
+  p.bias = e->bias;
+  p.rowvec = reinterpret_cast<const __half*>(e->rowvec);
+  p.rows_per_vec = e->rows_per_vec > 0 ? e->rows_per_vec : 1;
+  p.ld_rowvec = e->ld_rowvec;
+  p.residual = reinterpret_cast<const __half*>(e->residual);
+  p.ld_res = e->ld_res;
+  p.act = e->act;
+  p.out_dtype = e->out_dtype;
+  p.ld_out = e->ld_out;
+  p.out = d.out;
+  UAV_REQUIRE(p.ld_out >= p.n_out, "igemm: ld_out (%lld) < output columns (%d)",
+              (long long)p.ld_out, p.n_out);
+  UAV_REQUIRE(e->out_dtype == UAV_F16 || e->out_dtype == UAV_F32, "igemm: bad out_dtype");
+  UAV_REQUIRE(e->act == UAV_ACT_NONE || e->act == UAV_ACT_SILU || e->act == UAV_ACT_GEGLU,
+              "igemm: bad activation");
+  if (p.num_tiles == 0) return UAV_OK;
+
+  if (geglu) return launch_instance<256, true>(p, stream);
+  switch (block_n) {
+    case 256: return launch_instance<256, false>(p, stream);
+    case 128: return launch_instance<128, false>(p, stream);
+    case 64: return launch_instance<64, false>(p, stream);
+    case 32: return launch_instance<32, false>(p, stream);
+    default: return launch_instance<16, false>(p, stream);
+  }
+}
+
+// choose the (tw, th) rectangle with tw * th == 128 that wastes the fewest rows
+static void pick_tile_2d(int64_t W, int64_t H, uint32_t* tw, uint32_t* th) {
+  int64_t best = -1;
+  for (uint32_t w = 128; w >= 1; w >>= 1) {
+    const uint32_t h = 128 / w;
+    const int64_t cover = ((W + w - 1) / w) * w * ((H + h - 1) / h) * h;
+    if (best < 0 || cover < best) {
+      best = cover;
+      *tw = w;
+      *th = h;
+    }
+  }
+}
+
+}  // namespace uav
+
+using namespace uav;
+
+extern "C" {
+
+const char* uav_version(void) { return "uav_b200 0.1 (sm_100a)"; }
+const char* uav_last_error_string(void) { return g_err; }
+uint64_t uav_launch_count(void) { return g_launches.load(); }
+
+uav_status_t uav_linear(const void* a, int64_t M, int64_t K, int64_t lda, const void* w,
+                        int64_t N, void* out, const uav_epilogue_t* epi, uav_stream_t stream) {
+  UAV_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K, "uav_linear: bad shape");
+  if (M == 0) return UAV_OK;
+  IgemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = a;
+  const uint64_t dims[5] = {(uint64_t)K, (uint64_t)M, 1, 1, 1};
+  const uint64_t strides[5] = {1, (uint64_t)lda, (uint64_t)lda * M, (uint64_t)lda * M,
+                               (uint64_t)lda * M};
+  const uint32_t box[5] = {64, 128, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) {
+    d.a_dims[i] = dims[i];
+    d.a_strides[i] = strides[i];
+    d.box[i] = box[i];
+    d.tiles[i] = 1;
+    d.out_dims[i] = 1;
+  }
+  d.tiles[1] = (uint32_t)((M + 127) / 128);
+  d.out_dims[1] = (uint32_t)M;
+  d.num_taps = 1;
+  d.k_per_tap = (int)K;
+  d.w = w;
+  d.N = N;
+  d.out = out;
+  d.epi = epi;
+  return launch_igemm(d, (cudaStream_t)stream);
+}
+
+uav_status_t uav_conv2d(const void* x, int64_t NB, int64_t H, int64_t W, int64_t Cin,
+                        int64_t ld_in, const void* w, int64_t Cout, int ksize, int stride,
+                        int pad_mode, void* out, const uav_epilogue_t* epi,
+                        uav_stream_t stream) {
+  UAV_REQUIRE(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && ld_in >= Cin,
+              "uav_conv2d: bad shape");
+  UAV_REQUIRE(ksize == 1 || ksize == 3, "uav_conv2d: ksize must be 1 or 3");
+  UAV_REQUIRE(stride == 1 || stride == 2, "uav_conv2d: stride must be 1 or 2");
+  UAV_REQUIRE(pad_mode == 0 || (pad_mode == 1 && stride == 2 && ksize == 3),
+              "uav_conv2d: pad_mode 1 needs a stride-2 3x3 conv");
+  IgemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = x;
+  d.w = w;
+  d.N = Cout;
+  d.out = out;
+  d.epi = epi;
+  d.k_per_tap = (int)Cin;
+  const int pad = ksize / 2;
+  if (stride == 1) {
+    uint32_t tw, th;
+    pick_tile_2d(W, H, &tw, &th);
+    const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 1};
+    const uint64_t strides[5] = {1, (uint64_t)ld_in, (uint64_t)ld_in * W,
+                                 (uint64_t)ld_in * W * H, (uint64_t)ld_in * W * H * NB};
+    const uint32_t box[5] = {64, tw, th, 1, 1};
+    const uint32_t tiles[5] = {1, (uint32_t)((W + tw - 1) / tw), (uint32_t)((H + th - 1) / th),
+                               (uint32_t)NB, 1};
+    const uint32_t odims[5] = {1, (uint32_t)W, (uint32_t)H, (uint32_t)NB, 1};
+    for (int i = 0; i < 5; ++i) {
+      d.a_dims[i] = dims[i];
+      d.a_strides[i] = strides[i];
+      d.box[i] = box[i];
+      d.tiles[i] = tiles[i];
+      d.out_dims[i] = odims[i];
+    }
+    d.num_taps = ksize * ksize;
+    for (int ky = 0; ky < ksize; ++ky)
+      for (int kx = 0; kx < ksize; ++kx) {
+        int32_t* o = d.tap_off[ky * ksize + kx];
+        o[0] = 0;
+        o[1] = kx - pad;
+        o[2] = ky - pad;
+        o[3] = 0;
+        o[4] = 0;
+      }
+  } else {
+    UAV_REQUIRE(H % 2 == 0 && W % 2 == 0, "uav_conv2d: stride 2 needs even H, W (got %lldx%lld)",
+                (long long)H, (long long)W);
+    UAV_REQUIRE(ld_in == Cin, "uav_conv2d: stride 2 needs a dense input (ld_in == Cin)");
+    const int64_t Wo = W / 2, Ho = H / 2;
+    uint32_t tw, th;
+    pick_tile_2d(Wo, Ho, &tw, &th);
+    // phase view: (2C [px*C + c], W/2, 2 [py], H/2, NB)
+    const uint64_t dims[5] = {(uint64_t)(2 * Cin), (uint64_t)Wo, 2, (uint64_t)Ho, (uint64_t)NB};
+    const uint64_t strides[5] = {1, (uint64_t)(2 * Cin), (uint64_t)(W * Cin),
+                                 (uint64_t)(2 * W * Cin), (uint64_t)(H * W * Cin)};
+    const uint32_t box[5] = {64, tw, 1, th, 1};
+    const uint32_t tiles[5] = {1, (uint32_t)((Wo + tw - 1) / tw), 1,
+                               (uint32_t)((Ho + th - 1) / th), (uint32_t)NB};
+    const uint32_t odims[5] = {1, (uint32_t)Wo, 1, (uint32_t)Ho, (uint32_t)NB};
+    for (int i = 0; i < 5; ++i) {
+      d.a_dims[i] = dims[i];
+      d.a_strides[i] = strides[i];
+      d.box[i] = box[i];
+      d.tiles[i] = tiles[i];
+      d.out_dims[i] = odims[i];
+    }
+    d.num_taps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        // input coordinate = 2*o + k - pad  (pad = 1 for pad_mode 0, 0 for pad_mode 1)
+        const int iy = ky - (pad_mode == 0 ? 1 : 0);  // in {-1,0,1} or {0,1,2}
+        const int ix = kx - (pad_mode == 0 ? 1 : 0);
+        const int py = ((iy % 2) + 2) % 2, px = ((ix % 2) + 2) % 2;
+        const int oy = (iy - py) / 2, ox = (ix - px) / 2;  // exact
+        int32_t* o = d.tap_off[ky * 3 + kx];
+        o[0] = px * (int)Cin;
+        o[1] = ox;
+        o[2] = py;
+        o[3] = oy;
+        o[4] = 0;
+      }
+  }
+  return launch_igemm(d, (cudaStream_t)stream);
+}
+
+uav_status_t uav_conv_temporal(const void* x, int64_t B, int64_t T, int64_t HW, int64_t Cin,
+                               int64_t ld_in, const void* w, int64_t Cout, int k, void* out,
+                               const uav_epilogue_t* epi, uav_stream_t stream) {
+  UAV_REQUIRE(B > 0 && T > 0 && HW > 0 && Cin > 0 && Cout > 0 && ld_in >= Cin,
+              "uav_conv_temporal: bad shape");
+  UAV_REQUIRE(k == 1 || k == 3 || k == 5, "uav_conv_temporal: k must be 1, 3 or 5");
+  IgemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = x;
+  d.w = w;
+  d.N = Cout;
+  d.out = out;
+  d.epi = epi;
+  d.k_per_tap = (int)Cin;
+  const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)HW, (uint64_t)T, (uint64_t)B, 1};
+  const uint64_t strides[5] = {1, (uint64_t)ld_in, (uint64_t)ld_in * HW, (uint64_t)ld_in * HW * T,
+                               (uint64_t)ld_in * HW * T * B};
+  const uint32_t box[5] = {64, 128, 1, 1, 1};
+  const uint32_t tiles[5] = {1, (uint32_t)((HW + 127) / 128), (uint32_t)T, (uint32_t)B, 1};
+  const uint32_t odims[5] = {1, (uint32_t)HW, (uint32_t)T, (uint32_t)B, 1};
+  for (int i = 0; i < 5; ++i) {
+    d.a_dims[i] = dims[i];
+    d.a_strides[i] = strides[i];
+    d.box[i] = box[i];
+    d.tiles[i] = tiles[i];
+    d.out_dims[i] = odims[i];
+  }
+  d.num_taps = k;
+  for (int kt = 0; kt < k; ++kt) {
+    int32_t* o = d.tap_off[kt];
+    o[0] = 0;
+    o[1] = 0;
+    o[2] = kt - k / 2;
+    o[3] = 0;
+    o[4] = 0;
+  }
+  return launch_igemm(d, (cudaStream_t)stream);
+}
+
+uav_status_t uav_conv3d(const void* x, int64_t B, int64_t T, int64_t H, int64_t W, int64_t Cin,
+                        int64_t ld_in, const void* w, int64_t Cout, void* out,
+                        const uav_epilogue_t* epi, uav_stream_t stream) {
+  UAV_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && ld_in >= Cin,
+              "uav_conv3d: bad shape");
+  IgemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = x;
+  d.w = w;
+  d.N = Cout;
+  d.out = out;
+  d.epi = epi;
+  d.k_per_tap = (int)Cin;
+  uint32_t tw, th;
+  pick_tile_2d(W, H, &tw, &th);
+  const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)B};
+  const uint64_t strides[5] = {1, (uint64_t)ld_in, (uint64_t)ld_in * W, (uint64_t)ld_in * W * H,
+                               (uint64_t)ld_in * W * H * T};
+  const uint32_t box[5] = {64, tw, th, 1, 1};
+  const uint32_t tiles[5] = {1, (uint32_t)((W + tw - 1) / tw), (uint32_t)((H + th - 1) / th),
+                             (uint32_t)T, (uint32_t)B};
+  const uint32_t odims[5] = {1, (uint32_t)W, (uint32_t)H, (uint32_t)T, (uint32_t)B};
+  for (int i = 0; i < 5; ++i) {
+    d.a_dims[i] = dims[i];
+    d.a_strides[i] = strides[i];
+    d.box[i] = box[i];
+    d.tiles[i] = tiles[i];
+    d.out_dims[i] = odims[i];
+  }
+  d.num_taps = 27;
+  for (int kt = 0; kt < 3; ++kt)
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        int32_t* o = d.tap_off[(kt * 3 + ky) * 3 + kx];
+        o[0] = 0;
+        o[1] = kx - 1;
+        o[2] = ky - 1;
+        o[3] = kt - 1;
+        o[4] = 0;
+      }
+  return launch_igemm(d, (cudaStream_t)stream);
+}
+
+}  // extern "C"
