@@ -72,12 +72,15 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // fp16 elements: one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int MAX_TAPS = 27;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int NUM_EPI_THREADS = 256;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int SLAB_BYTES = BLOCK_M * 128;  // 128 rows x 64 fp16 output columns, 128B-swizzled
 
 struct alignas(64) IgemmParams {
   CUtensorMap map_a;
   CUtensorMap map_b;
+  CUtensorMap map_out;           // only valid when tma_store != 0
   int32_t tap_off[MAX_TAPS][5];  // coordinate offset of each tap (dim0 = channel offset)
   int32_t num_taps;
   int32_t kblocks_per_tap;
@@ -88,6 +91,7 @@ struct alignas(64) IgemmParams {
   uint32_t n_tiles, num_tiles;
   int32_t N;      // rows of B
   int32_t n_out;  // output columns (N, or N/2 with GEGLU)
+  int32_t tma_store;
   const float* bias;
   const __half* rowvec;
   int64_t rows_per_vec, ld_rowvec;
@@ -98,49 +102,70 @@ struct alignas(64) IgemmParams {
   void* out;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool GEGLU>
 struct IgemmCfg {
+  static constexpr int OUT_TILE_N = GEGLU ? BLOCK_N / 2 : BLOCK_N;
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGING_BYTES = (OUT_TILE_N >= 64) ? (OUT_TILE_N / 64) * SLAB_BYTES : 0;
+  static constexpr int AUX_BYTES = 2048;  // barriers + tmem slot + bias tile (256 floats)
+  static constexpr int STAGES_RAW = (232448 - 1024 - STAGING_BYTES - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
                                    : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256
                                                           : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + AUX_BYTES + 1024 /*align*/;
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+}
+__device__ __forceinline__ void add_half8(float (&x)[8], const uint4& q) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h2[j]);
+    x[2 * j] += f.x;
+    x[2 * j + 1] += f.y;
+  }
+}
 
 template <int BLOCK_N, bool GEGLU>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     igemm_kernel(const __grid_constant__ IgemmParams p) {
-  using Cfg = IgemmCfg<BLOCK_N>;
+  using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int OUT_TILE_N = Cfg::OUT_TILE_N;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (SWIZZLE_128B atoms) in the shared address space
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* aux = staging + Cfg::STAGING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* sbias = reinterpret_cast<float*>(aux + 512);  // [BLOCK_N]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool tma_store = (OUT_TILE_N >= 64) && p.tma_store != 0;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
+    if (tma_store) tma_prefetch_desc(&p.map_out);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -149,8 +174,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 4);
-    mbar_init(&tempty_bar[1], 4);
+    mbar_init(&tempty_bar[0], tma_store ? 8 : 4);
+    mbar_init(&tempty_bar[1], tma_store ? 8 : 4);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -236,7 +261,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp_idx >= 4) {
     // =============================== epilogue ===============================
-    const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp_idx & 3;        // TMEM lane quadrant this warp may access
+    const int half = (warp_idx - 4) >> 2;  // column half handled by this warp (TMA-store path)
+    const int et = threadIdx.x - 128;      // 0..255
     const uint32_t row = quad * 32 + lane;
     uint32_t r = row;
     const uint32_t l1 = r % p.box[1];
@@ -246,145 +273,228 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t l3 = r % p.box[3];
     r /= p.box[3];
     const uint32_t l4 = r;
-    const bool vec_ok = (p.ld_out % 8 == 0) && (p.n_out % 8 == 0) &&
-                        (p.residual == nullptr || p.ld_res % 8 == 0) &&
-                        (p.rowvec == nullptr || p.ld_rowvec % 8 == 0);
-    constexpr int OUT_TILE_N = GEGLU ? BLOCK_N / 2 : BLOCK_N;
-    constexpr int CHUNK = (OUT_TILE_N >= 32) ? 32 : 16;
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const uint32_t n_tile = tile % p.n_tiles;
-      uint32_t idx = tile / p.n_tiles;
-      const uint32_t o1 = (idx % p.tiles[1]) * p.box[1] + l1;
-      idx /= p.tiles[1];
-      const uint32_t o2 = (idx % p.tiles[2]) * p.box[2] + l2;
-      idx /= p.tiles[2];
-      const uint32_t o3 = (idx % p.tiles[3]) * p.box[3] + l3;
-      idx /= p.tiles[3];
-      const uint32_t o4 = idx * p.box[4] + l4;
-      const bool row_ok = o1 < p.out_dims[1] && o2 < p.out_dims[2] && o3 < p.out_dims[3] &&
-                          o4 < p.out_dims[4];
-      const int64_t out_row =
-          ((static_cast<int64_t>(o4) * p.out_dims[3] + o3) * p.out_dims[2] + o2) * p.out_dims[1] +
-          o1;
-      const __half* rv =
-          (p.rowvec != nullptr && row_ok) ? p.rowvec + (out_row / p.rows_per_vec) * p.ld_rowvec
-                                          : nullptr;
-      const __half* res = (p.residual != nullptr && row_ok) ? p.residual + out_row * p.ld_res
-                                                            : nullptr;
+    if (tma_store || half == 0) {
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const uint32_t n_tile = tile % p.n_tiles;
+        uint32_t idx = tile / p.n_tiles;
+        const uint32_t t1 = (idx % p.tiles[1]) * p.box[1];
+        idx /= p.tiles[1];
+        const uint32_t t2 = (idx % p.tiles[2]) * p.box[2];
+        idx /= p.tiles[2];
+        const uint32_t t3 = (idx % p.tiles[3]) * p.box[3];
+        idx /= p.tiles[3];
+        const uint32_t t4 = idx * p.box[4];
+        const uint32_t o1 = t1 + l1, o2 = t2 + l2, o3 = t3 + l3, o4 = t4 + l4;
+        const bool row_ok = o1 < p.out_dims[1] && o2 < p.out_dims[2] && o3 < p.out_dims[3] &&
+                            o4 < p.out_dims[4];
+        const int64_t out_row =
+            ((static_cast<int64_t>(o4) * p.out_dims[3] + o3) * p.out_dims[2] + o2) *
+                p.out_dims[1] + o1;
+        const __half* rv = (p.rowvec != nullptr && row_ok)
+                               ? p.rowvec + (out_row / p.rows_per_vec) * p.ld_rowvec
+                               : nullptr;
+        const __half* res =
+            (p.residual != nullptr && row_ok) ? p.residual + out_row * p.ld_res : nullptr;
+        const int n_base = n_tile * OUT_TILE_N;
+        const uint32_t taddr =
+            tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
-
+        if (tma_store) {
+          if constexpr (OUT_TILE_N >= 64) {
+            // ---- stage the bias tile, make sure the previous TMA store released the staging ----
+            if (GEGLU) {
+              const int j = et & (OUT_TILE_N - 1);
+              const int n = (et < OUT_TILE_N) ? (n_base + j) : (p.N / 2 + n_base + j);
+              sbias[et] = (p.bias != nullptr && n_base + j < p.n_out) ? __ldg(p.bias + n) : 0.f;
+            } else if (et < OUT_TILE_N) {
+              sbias[et] = (p.bias != nullptr && n_base + et < p.n_out) ? __ldg(p.bias + n_base + et)
+                                                                       : 0.f;
+            }
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            epi_bar_sync();
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            constexpr int COLS_PER_HALF = OUT_TILE_N / 2;
+            constexpr int CHUNKS = COLS_PER_HALF / 32;
 #pragma unroll 1
-      for (int c = 0; c < OUT_TILE_N / CHUNK; ++c) {
-        float v[CHUNK];
-        if constexpr (CHUNK == 32) {
-          uint32_t a[32];
-          tmem_ld_32x32(taddr + c * 32, a);
-          if constexpr (GEGLU) {
-            uint32_t g[32];
-            tmem_ld_32x32(taddr + BLOCK_N / 2 + c * 32, g);
-            tmem_ld_wait();
-            const int n0 = n_tile * OUT_TILE_N + c * 32;
+            for (int c = 0; c < CHUNKS; ++c) {
+              const int col0 = half * COLS_PER_HALF + c * 32;  // column inside the output tile
+              const int n0 = n_base + col0;
+              const bool cols_ok = n0 < p.n_out;  // n_out % 8 == 0; groups of 8 checked below
+              // issue the global loads first so their latency overlaps the TMEM load
+              uint4 rq[4], vq[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float h = __uint_as_float(a[j]);
-              float gg = __uint_as_float(g[j]);
-              if (p.bias != nullptr) {
-                h += __ldg(p.bias + n0 + j);
-                gg += __ldg(p.bias + p.N / 2 + n0 + j);
+              for (int g = 0; g < 4; ++g) {
+                rq[g] = make_uint4(0, 0, 0, 0);
+                vq[g] = make_uint4(0, 0, 0, 0);
+                if (cols_ok && n0 + g * 8 < p.n_out) {
+                  if (res != nullptr) rq[g] = ldg16(res + n0 + g * 8);
+                  if (rv != nullptr) vq[g] = ldg16(rv + n0 + g * 8);
+                }
               }
-              v[j] = h * gelu_erf_f(gg);
-            }
-          } else {
-            tmem_ld_wait();
+              uint32_t a[32];
+              tmem_ld_32x32(taddr + col0, a);
+              float v[32];
+              if constexpr (GEGLU) {
+                uint32_t gt[32];
+                tmem_ld_32x32(taddr + BLOCK_N / 2 + col0, gt);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]);
+                for (int j = 0; j < 32; ++j) {
+                  const float hh = __uint_as_float(a[j]) + sbias[col0 + j];
+                  const float gg = __uint_as_float(gt[j]) + sbias[OUT_TILE_N + col0 + j];
+                  v[j] = hh * gelu_erf_f(gg);
+                }
+              } else {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) + sbias[col0 + j];
+              }
+              const int slab = col0 >> 6;
+              const int chunk_base = (col0 & 63) >> 3;  // 16-byte chunk index inside the 128B row
+              uint8_t* srow = staging + slab * SLAB_BYTES + row * 128;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j];
+                if (rv != nullptr) add_half8(x, vq[g]);
+                if (p.act == UAV_ACT_SILU) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+                }
+                if (res != nullptr) add_half8(x, rq[g]);
+                uint4 o;
+                o.x = pack_half2(x[0], x[1]);
+                o.y = pack_half2(x[2], x[3]);
+                o.z = pack_half2(x[4], x[5]);
+                o.w = pack_half2(x[6], x[7]);
+                const int phys = (chunk_base + g) ^ (row & 7);  // CU_TENSOR_MAP_SWIZZLE_128B
+                *reinterpret_cast<uint4*>(srow + phys * 16) = o;
+              }
+            }
+            // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            // publish the staged tile to the async proxy and store it with TMA (clips OOB rows)
+            fence_proxy_async();
+            epi_bar_sync();
+            if (et == 0) {
+#pragma unroll
+              for (int sl = 0; sl < OUT_TILE_N / 64; ++sl) {
+                if (n_base + sl * 64 < p.n_out) {
+                  asm volatile(
+                      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group"
+                      " [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                          reinterpret_cast<uint64_t>(&p.map_out)),
+                      "r"(smem_u32(staging + sl * SLAB_BYTES)), "r"(n_base + sl * 64), "r"(t1),
+                      "r"(t2), "r"(t3), "r"(t4)
+                      : "memory");
+                }
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
           }
         } else {
-          uint32_t a[16];
-          tmem_ld_32x16(taddr + c * 16, a);
-          tmem_ld_wait();
+          // ---- direct path (small N, fp32 output, unaligned): 4 warps, per-row stores ----
+          constexpr int CHUNK = (OUT_TILE_N >= 32) ? 32 : 16;
+          const bool vec_ok = (p.ld_out % 8 == 0) && (p.n_out % 8 == 0) &&
+                              (p.residual == nullptr || p.ld_res % 8 == 0) &&
+                              (p.rowvec == nullptr || p.ld_rowvec % 8 == 0);
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < OUT_TILE_N / CHUNK; ++c) {
+            const int n0 = n_base + c * CHUNK;
+            uint32_t a[CHUNK];
+            float v[CHUNK];
+            if constexpr (CHUNK == 32) {
+              tmem_ld_32x32(taddr + c * 32, a);
+              if constexpr (GEGLU) {
+                uint32_t gt[32];
+                tmem_ld_32x32(taddr + BLOCK_N / 2 + c * 32, gt);
+                tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]);
-        }
-        const int n0 = n_tile * OUT_TILE_N + c * CHUNK;
-        if (!row_ok || n0 >= p.n_out) continue;
-        if (vec_ok) {
-          // all 8-column groups are either fully valid or fully out of range
+                for (int j = 0; j < 32; ++j) {
+                  float hh = __uint_as_float(a[j]), gg = __uint_as_float(gt[j]);
+                  if (p.bias != nullptr && n0 + j < p.n_out) {
+                    hh += __ldg(p.bias + n0 + j);
+                    gg += __ldg(p.bias + p.N / 2 + n0 + j);
+                  }
+                  v[j] = hh * gelu_erf_f(gg);
+                }
+              } else {
+                tmem_ld_wait();
 #pragma unroll
-          for (int g8 = 0; g8 < CHUNK / 8; ++g8) {
-            const int n = n0 + g8 * 8;
-            if (n >= p.n_out) break;
-            float x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = v[g8 * 8 + j];
-            if (!GEGLU && p.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-            }
-            if (rv != nullptr) {
-              const uint4 q = ldg16(rv + n);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                x[2 * j] += f.x;
-                x[2 * j + 1] += f.y;
+                for (int j = 0; j < 32; ++j) {
+                  v[j] = __uint_as_float(a[j]);
+                  if (p.bias != nullptr && n0 + j < p.n_out) v[j] += __ldg(p.bias + n0 + j);
+                }
               }
-            }
-            if (p.act == UAV_ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
-            }
-            if (res != nullptr) {
-              const uint4 q = ldg16(res + n);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                x[2 * j] += f.x;
-                x[2 * j + 1] += f.y;
-              }
-            }
-            if (p.out_dtype == UAV_F16) {
-              uint4 o;
-              o.x = pack_half2(x[0], x[1]);
-              o.y = pack_half2(x[2], x[3]);
-              o.z = pack_half2(x[4], x[5]);
-              o.w = pack_half2(x[6], x[7]);
-              stg16(reinterpret_cast<__half*>(p.out) + out_row * p.ld_out + n, o);
             } else {
-              float* op = reinterpret_cast<float*>(p.out) + out_row * p.ld_out + n;
-              *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
-              *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              tmem_ld_32x16(taddr + c * 16, a);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                v[j] = __uint_as_float(a[j]);
+                if (p.bias != nullptr && n0 + j < p.n_out) v[j] += __ldg(p.bias + n0 + j);
+              }
+            }
+            if (!row_ok || n0 >= p.n_out) continue;
+            if (vec_ok) {
+#pragma unroll
+              for (int g8 = 0; g8 < CHUNK / 8; ++g8) {
+                const int n = n0 + g8 * 8;
+                if (n < p.n_out) {
+                  float x[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) x[j] = v[g8 * 8 + j];
+                  if (rv != nullptr) add_half8(x, ldg16(rv + n));
+                  if (p.act == UAV_ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+                  }
+                  if (res != nullptr) add_half8(x, ldg16(res + n));
+                  if (p.out_dtype == UAV_F16) {
+                    uint4 o;
+                    o.x = pack_half2(x[0], x[1]);
+                    o.y = pack_half2(x[2], x[3]);
+                    o.z = pack_half2(x[4], x[5]);
+                    o.w = pack_half2(x[6], x[7]);
+                    stg16(reinterpret_cast<__half*>(p.out) + out_row * p.ld_out + n, o);
+                  } else {
+                    float* op = reinterpret_cast<float*>(p.out) + out_row * p.ld_out + n;
+                    *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) {
+                const int n = n0 + j;
+                if (n < p.n_out) {
+                  float x = v[j];
+                  if (rv != nullptr) x += __half2float(rv[n]);
+                  if (p.act == UAV_ACT_SILU) x = silu_f(x);
+                  if (res != nullptr) x += __half2float(res[n]);
+                  if (p.out_dtype == UAV_F16)
+                    reinterpret_cast<__half*>(p.out)[out_row * p.ld_out + n] = __float2half_rn(x);
+                  else
+                    reinterpret_cast<float*>(p.out)[out_row * p.ld_out + n] = x;
+                }
+              }
             }
           }
-        } else {
-          for (int j = 0; j < CHUNK; ++j) {
-            const int n = n0 + j;
-            if (n >= p.n_out) break;
-            float x = v[j];
-            if (!GEGLU && p.bias != nullptr) x += __ldg(p.bias + n);
-            if (rv != nullptr) x += __half2float(rv[n]);
-            if (p.act == UAV_ACT_SILU) x = silu_f(x);
-            if (res != nullptr) x += __half2float(res[n]);
-            if (p.out_dtype == UAV_F16)
-              reinterpret_cast<__half*>(p.out)[out_row * p.ld_out + n] = __float2half_rn(x);
-            else
-              reinterpret_cast<float*>(p.out)[out_row * p.ld_out + n] = x;
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
       }
-      // release this accumulator to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
 
@@ -419,7 +529,7 @@ struct IgemmDesc {
 
 template <int BLOCK_N, bool GEGLU>
 static uav_status_t launch_instance(IgemmParams& p, cudaStream_t stream) {
-  using Cfg = IgemmCfg<BLOCK_N>;
+  using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
   static bool configured = false;
   if (!configured) {
     UAV_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, GEGLU>,
@@ -530,6 +640,32 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   UAV_REQUIRE(e->act == UAV_ACT_NONE || e->act == UAV_ACT_SILU || e->act == UAV_ACT_GEGLU,
               "igemm: bad activation");
   if (p.num_tiles == 0) return UAV_OK;
+
+  // TMA-store epilogue (smem-staged, fully coalesced, clips partial tiles) whenever the output
+  // is an aligned fp16 tensor with at least 64-column tiles; otherwise per-row direct stores.
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool can_tma = out_tile_n >= 64 && e->out_dtype == UAV_F16 && p.n_out % 8 == 0 &&
+                       p.ld_out % 8 == 0 && aligned16(d.out) &&
+                       (p.residual == nullptr || (p.ld_res % 8 == 0 && aligned16(p.residual))) &&
+                       (p.rowvec == nullptr || (p.ld_rowvec % 8 == 0 && aligned16(p.rowvec)));
+  p.tma_store = can_tma ? 1 : 0;
+  if (can_tma) {
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    dims[0] = (cuuint64_t)p.n_out;
+    box[0] = 64;
+    uint64_t stride_el = (uint64_t)p.ld_out;
+    for (int i = 1; i < 5; ++i) {
+      dims[i] = d.out_dims[i];
+      box[i] = d.box[i];
+      strides[i - 1] = stride_el * 2;
+      stride_el *= d.out_dims[i];
+    }
+    CUresult r = encode(&p.map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, d.out, dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAV_REQUIRE(r == CUDA_SUCCESS, "igemm: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+  }
 
   if (geglu) return launch_instance<256, true>(p, stream);
   switch (block_n) {

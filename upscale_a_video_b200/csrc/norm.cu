@@ -1,0 +1,339 @@
+// norm.cu — GroupNorm(+SiLU) over channels-last video tensors and LayerNorm over tokens.
+// HBM-bound kernels: 128-bit coalesced loads, fp32 statistics
+// (fp64 for the cross-block accumulation), fused affine + SiLU on the way out.
+//
+// GroupNorm semantics follow nn.GroupNorm applied to the reference's 5-D "b c t h w" tensors
+// (resnet.py:231,267,278): one (mean, var) per (batch item, group) over (C/G)*T*H*W elements —
+// statistics span all frames of the chunk.  The per-frame 4-D case (attention.py:374,
+// AttentionBlock) is the same kernel with n_outer = b*t and pixels = h*w.
+#include "uav_common.cuh"
+
+#include <atomic>
+
+namespace uav {
+extern std::atomic<uint64_t> g_launches;
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_UNITS = 512;  // 4-channel units: C <= 2048
+
+// ---------------------------------------------------------------------------------------
+// stats: sums[n][g] = {sum, sumsq} (fp64) over the group's channels and all pixels
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_THREADS)
+    gn_stats_kernel(const __half* __restrict__ x, int64_t pixels, int C, int64_t ld, int G,
+                    double* __restrict__ sums) {
+  __shared__ float s_sum[GN_MAX_UNITS];
+  __shared__ float s_sq[GN_MAX_UNITS];
+  const int n = blockIdx.y;
+  const int octs = C >> 3;  // 8-channel vectors per pixel
+  const int units = C >> 2;
+  for (int i = threadIdx.x; i < units; i += GN_THREADS) {
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  __syncthreads();
+  const __half* xn = x + static_cast<int64_t>(n) * pixels * ld;
+  // thread -> (pixel lane, octet); octs may exceed the block (C = 2048 -> 256 octets)
+  const int oct_per_pass = octs < GN_THREADS ? octs : GN_THREADS;
+  const int pix_per_iter = GN_THREADS / oct_per_pass;
+  const int my_pix = threadIdx.x / oct_per_pass;
+  const int my_oct0 = threadIdx.x % oct_per_pass;
+  if (my_pix < pix_per_iter) {
+    for (int oct = my_oct0; oct < octs; oct += oct_per_pass) {
+      float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
+      for (int64_t p = static_cast<int64_t>(blockIdx.x) * pix_per_iter + my_pix; p < pixels;
+           p += static_cast<int64_t>(gridDim.x) * pix_per_iter) {
+        const uint4 v = ldg16(xn + p * ld + oct * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+        const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+        a0 += f0.x + f0.y + f1.x + f1.y;
+        q0 += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;
+        a1 += f2.x + f2.y + f3.x + f3.y;
+        q1 += f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
+      }
+      atomicAdd(&s_sum[oct * 2], a0);
+      atomicAdd(&s_sq[oct * 2], q0);
+      atomicAdd(&s_sum[oct * 2 + 1], a1);
+      atomicAdd(&s_sq[oct * 2 + 1], q1);
+    }
+  }
+  __syncthreads();
+  const int units_per_group = units / G;  // (C/G)/4
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    double s = 0.0, q = 0.0;
+    for (int u = 0; u < units_per_group; ++u) {
+      s += s_sum[g * units_per_group + u];
+      q += s_sq[g * units_per_group + u];
+    }
+    atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2], s);
+    atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2 + 1], q);
+  }
+}
+
+// generic scalar statistics (any C, any G): used for tiny channel counts (C = 3)
+__global__ void __launch_bounds__(GN_THREADS)
+    gn_stats_generic_kernel(const __half* __restrict__ x, int64_t pixels, int C, int64_t ld, int G,
+                            double* __restrict__ sums) {
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const __half* xn = x + static_cast<int64_t>(n) * pixels * ld;
+  for (int g = 0; g < G; ++g) {
+    float s = 0.f, q = 0.f;
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * GN_THREADS + threadIdx.x; p < pixels;
+         p += static_cast<int64_t>(gridDim.x) * GN_THREADS) {
+      for (int c = 0; c < cpg; ++c) {
+        const float v = __half2float(xn[p * ld + g * cpg + c]);
+        s += v;
+        q += v * v;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffff, s, o);
+      q += __shfl_xor_sync(0xffffffff, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2], static_cast<double>(s));
+      atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2 + 1], static_cast<double>(q));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// apply: y = (x - mean) * rstd * gamma + beta, optional SiLU; fp16 out
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_THREADS)
+    gn_apply_kernel(const __half* __restrict__ x, int64_t pixels, int C, int64_t ld_in, int G,
+                    const double* __restrict__ sums, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, int silu, __half* __restrict__ y,
+                    int64_t ld_out) {
+  extern __shared__ float s_aff[];  // [C] scale, [C] shift
+  float* s_scale = s_aff;
+  float* s_shift = s_aff + C;
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const double cnt = static_cast<double>(pixels) * cpg;
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cpg;
+    const double s = sums[(static_cast<int64_t>(n) * G + g) * 2];
+    const double q = sums[(static_cast<int64_t>(n) * G + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * rstd;
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  }
+  __syncthreads();
+  const __half* xn = x + static_cast<int64_t>(n) * pixels * ld_in;
+  __half* yn = y + static_cast<int64_t>(n) * pixels * ld_out;
+  if ((C & 7) == 0) {
+    const int octs = C >> 3;
+    const int64_t total = pixels * octs;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * GN_THREADS) {
+      const int64_t p = i / octs;
+      const int oct = static_cast<int>(i - p * octs);
+      const uint4 v = ldg16(xn + p * ld_in + oct * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        const int c = oct * 8 + 2 * j;
+        float a = f.x * s_scale[c] + s_shift[c];
+        float b = f.y * s_scale[c + 1] + s_shift[c + 1];
+        if (silu) {
+          a = silu_f(a);
+          b = silu_f(b);
+        }
+        __half2 r = __floats2half2_rn(a, b);
+        ow[j] = *reinterpret_cast<uint32_t*>(&r);
+      }
+      stg16(yn + p * ld_out + oct * 8, o);
+    }
+  } else {
+    const int64_t total = pixels * C;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * GN_THREADS) {
+      const int64_t p = i / C;
+      const int c = static_cast<int>(i - p * C);
+      float a = __half2float(xn[p * ld_in + c]) * s_scale[c] + s_shift[c];
+      if (silu) a = silu_f(a);
+      yn[p * ld_out + c] = __float2half_rn(a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over the last dim (C % 8 == 0, C <= 2048): one warp per token
+// ---------------------------------------------------------------------------------------
+template <int MAX_OCT>
+__global__ void __launch_bounds__(256)
+    layernorm_kernel(const __half* __restrict__ x, int64_t rows, int C, int64_t ld_in,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     __half* __restrict__ y, int64_t ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int octs = C >> 3;
+  uint4 v[MAX_OCT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_OCT; ++i) {
+    const int oct = lane + i * 32;
+    if (oct < octs) {
+      v[i] = ldg16(x + row * ld_in + oct * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s += f.x + f.y;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_OCT; ++i) {
+    const int oct = lane + i * 32;
+    if (oct < octs) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffff, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int i = 0; i < MAX_OCT; ++i) {
+    const int oct = lane + i * 32;
+    if (oct < octs) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + oct * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + oct * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + oct * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + oct * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        __half2 r = __floats2half2_rn((f.x - mean) * rstd * gg[2 * j] + bb[2 * j],
+                                      (f.y - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
+        ow[j] = *reinterpret_cast<uint32_t*>(&r);
+      }
+      stg16(y + row * ld_out + oct * 8, o);
+    }
+  }
+}
+
+}  // namespace uav
+
+using namespace uav;
+
+extern "C" {
+
+size_t uav_groupnorm_workspace_bytes(int64_t n_outer, int groups) {
+  return static_cast<size_t>(n_outer) * groups * 2 * sizeof(double);
+}
+
+uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, int64_t C,
+                                int64_t ld_in, int groups, const float* gamma, const float* beta,
+                                float eps, int silu, void* y, int64_t ld_out, void* workspace,
+                                size_t workspace_bytes, uav_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UAV_REQUIRE(x && y && gamma && beta && workspace, "uav_groupnorm_silu: null pointer");
+  UAV_REQUIRE(n_outer > 0 && pixels > 0 && C > 0 && groups > 0 && C % groups == 0 && ld_in >= C &&
+                  ld_out >= C,
+              "uav_groupnorm_silu: bad shape (C=%lld groups=%d)", (long long)C, groups);
+  UAV_REQUIRE(C <= 2048, "uav_groupnorm_silu: C > 2048 unsupported");
+  UAV_REQUIRE(n_outer <= 65535, "uav_groupnorm_silu: n_outer too large");
+  UAV_REQUIRE(workspace_bytes >= uav_groupnorm_workspace_bytes(n_outer, groups),
+              "uav_groupnorm_silu: workspace too small");
+  UAV_CHECK_CUDA(
+      cudaMemsetAsync(workspace, 0, uav_groupnorm_workspace_bytes(n_outer, groups), stream));
+  double* sums = reinterpret_cast<double*>(workspace);
+  const int cpg = (int)(C / groups);
+  const bool vec = (C % 8 == 0) && (cpg % 4 == 0) && (ld_in % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int sms = num_sms();
+  if (vec) {
+    const int octs = (int)(C / 8);
+    const int oct_per_pass = octs < GN_THREADS ? octs : GN_THREADS;
+    const int pix_per_iter = GN_THREADS / oct_per_pass;
+    int64_t want = (sms * 8 + n_outer - 1) / n_outer;
+    int64_t maxb = (pixels + pix_per_iter - 1) / pix_per_iter;
+    // at least ~16 pixels per thread-iteration chain to amortise the smem atomics
+    maxb = (maxb + 15) / 16;
+    int64_t gx = want < maxb ? want : maxb;
+    if (gx < 1) gx = 1;
+    gn_stats_kernel<<<dim3((unsigned)gx, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
+        reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums);
+  } else {
+    int64_t want = (sms * 4 + n_outer - 1) / n_outer;
+    int64_t maxb = (pixels + GN_THREADS - 1) / GN_THREADS;
+    int64_t gx = want < maxb ? want : maxb;
+    if (gx < 1) gx = 1;
+    gn_stats_generic_kernel<<<dim3((unsigned)gx, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
+        reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums);
+  }
+  UAV_CHECK_CUDA(cudaGetLastError());
+  {
+    const bool vec_apply = (C % 8 == 0) && (ld_in % 8 == 0) && (ld_out % 8 == 0) &&
+                           ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    UAV_REQUIRE(vec_apply || C % 8 != 0,
+                "uav_groupnorm_silu: C %% 8 == 0 tensors must be 16-byte aligned with ld %% 8 == 0");
+    const int64_t work = vec_apply ? pixels * (C / 8) : pixels * C;
+    int64_t want = (sms * 16 + n_outer - 1) / n_outer;
+    int64_t maxb = (work + GN_THREADS * 4 - 1) / (GN_THREADS * 4);
+    int64_t gx = want < maxb ? want : maxb;
+    if (gx < 1) gx = 1;
+    gn_apply_kernel<<<dim3((unsigned)gx, (unsigned)n_outer), GN_THREADS, 2 * C * sizeof(float),
+                      stream>>>(reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups,
+                                sums, gamma, beta, eps, silu, reinterpret_cast<__half*>(y),
+                                ld_out);
+  }
+  UAV_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return UAV_OK;
+}
+
+uav_status_t uav_layernorm(const void* x, int64_t rows, int64_t C, int64_t ld_in,
+                           const float* gamma, const float* beta, float eps, void* y,
+                           int64_t ld_out, uav_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UAV_REQUIRE(x && y && gamma && beta, "uav_layernorm: null pointer");
+  UAV_REQUIRE(rows >= 0 && C > 0 && C % 8 == 0 && C <= 2048 && ld_in >= C && ld_out >= C &&
+                  ld_in % 8 == 0 && ld_out % 8 == 0,
+              "uav_layernorm: bad shape (C=%lld)", (long long)C);
+  if (rows == 0) return UAV_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const int octs = (int)(C / 8);
+  if (octs <= 64)
+    layernorm_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), rows, (int)C,
+                                                  ld_in, gamma, beta, eps,
+                                                  reinterpret_cast<__half*>(y), ld_out);
+  else if (octs <= 128)
+    layernorm_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), rows, (int)C,
+                                                  ld_in, gamma, beta, eps,
+                                                  reinterpret_cast<__half*>(y), ld_out);
+  else
+    layernorm_kernel<8><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), rows, (int)C,
+                                                  ld_in, gamma, beta, eps,
+                                                  reinterpret_cast<__half*>(y), ld_out);
+  UAV_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return UAV_OK;
+}
+
+}  // extern "C"
