@@ -99,6 +99,113 @@ uav_status_t uav_conv3d(const void* x, int64_t B, int64_t T, int64_t H, int64_t 
                         int64_t ld_in, const void* w, int64_t Cout, void* out,
                         const uav_epilogue_t* epi, uav_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * normalisation
+ * ------------------------------------------------------------------------------------------- */
+/* bytes of caller-owned scratch needed by uav_groupnorm_silu (fp64 {sum, sumsq} per (n, group)) */
+size_t uav_groupnorm_workspace_bytes(int64_t n_outer, int groups);
+
+/* GroupNorm (+ optional SiLU) over channels-last data: x [n_outer][pixels][ld_in] fp16, statistics
+ * per (n_outer, group) over pixels * C/groups elements, fp32 affine, fp16 output.
+ * 5-D nn.GroupNorm of the reference ("b c t h w", resnet.py:231,247,267,278; unet_video.py:331,567):
+ * n_outer = b, pixels = t*h*w (statistics span the frames of the chunk).  Per-frame 4-D GroupNorm
+ * (attention.py:325,374; AttentionBlock diffusers_attention.py:269): n_outer = b*t, pixels = h*w.
+ * SiLU = the `nonlinearity` that always follows (resnet.py:268,284; unet_video.py:568). */
+uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, int64_t C,
+                                int64_t ld_in, int groups, const float* gamma, const float* beta,
+                                float eps, int silu, void* y, int64_t ld_out, void* workspace,
+                                size_t workspace_bytes, uav_stream_t stream);
+
+/* nn.LayerNorm over the last dim of fp16 tokens (attention.py:457,474,491,494). C % 8 == 0. */
+uav_status_t uav_layernorm(const void* x, int64_t rows, int64_t C, int64_t ld_in,
+                           const float* gamma, const float* beta, float eps, void* y,
+                           int64_t ld_out, uav_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * attention
+ * ------------------------------------------------------------------------------------------- */
+/* out = softmax(q k^T * scale) v per (batch, head), never materialising the scores
+ * (CrossAttention._attention attention.py:209-238; AttentionBlock diffusers_attention.py:330-381).
+ * q [batch][nq][ldq], k/v [batch / kv_batch_div][nk][ld], out [batch][nq][ldo]; head h occupies
+ * columns [h*head_dim, (h+1)*head_dim).  kv_batch_div = frames when the text K/V are shared by all
+ * frames of a batch item (the reference repeats them: attention.py:364).  head_dim 64, 128, or
+ * 512 (single head). */
+uav_status_t uav_attention(const void* q, const void* k, const void* v, void* out, int64_t batch,
+                           int heads, int head_dim, int64_t nq, int64_t nk, int64_t ldq,
+                           int64_t ldk, int64_t ldv, int64_t ldo, int64_t kv_batch_div,
+                           float scale, uav_stream_t stream);
+
+/* TemporalAttention._attention (attention.py:699-733): per pixel, sequence = frames (F <= 8);
+ * q is scaled, q and k get the rotary embedding on dims [0,32) (cos/sin table rot[F][16][2]),
+ * scores += rel_bias[heads][F][F], row-max subtract, softmax, PV.  Tokens are ordered
+ * (b, f, hw) — the channels-last video layout — so no rearrange copies are needed. */
+uav_status_t uav_temporal_attention(const void* q, const void* k, const void* v, void* out,
+                                    int64_t B, int64_t F, int64_t HW, int heads, int head_dim,
+                                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                    float scale, const float* rot_cos_sin, const float* rel_bias,
+                                    uav_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * data movement
+ * ------------------------------------------------------------------------------------------- */
+/* dst[p][0:C] = src[p][0:C] for `pixels` rows (torch.cat of skip connections, unet_blocks.py:573,645) */
+uav_status_t uav_copy_channels(const void* src, int64_t ld_src, void* dst, int64_t ld_dst,
+                               int64_t C, int64_t pixels, uav_stream_t stream);
+/* F.interpolate(mode="nearest") of NB channels-last images to (Ho, Wo) (Upsample3D resnet.py:143-146) */
+uav_status_t uav_upsample_nearest(const void* src, int64_t ld_src, int64_t NB, int64_t Hi,
+                                  int64_t Wi, int64_t C, void* dst, int64_t ld_dst, int64_t Ho,
+                                  int64_t Wo, uav_stream_t stream);
+/* API edge: reference layout (B, C, T*H*W) fp16/fp32 -> channels-last fp16 at channel offset c_off
+ * (also performs torch.cat([sample, low_res], dim=1), unet_video.py:440), times `scale`. */
+uav_status_t uav_planar_to_channels_last(const void* src, int src_dtype, int64_t B, int64_t C,
+                                         int64_t thw, void* dst, int64_t ld_dst, int64_t c_off,
+                                         float scale, uav_stream_t stream);
+/* API edge: channels-last -> (B, C, T*H*W); clamp != 0 applies .clamp(-1, 1) (pipeline...:353) */
+uav_status_t uav_channels_last_to_planar(const void* src, int src_dtype, int64_t ld_src, int64_t B,
+                                         int64_t C, int64_t thw, void* dst, int dst_dtype,
+                                         int clamp, uav_stream_t stream);
+uav_status_t uav_silu(const void* x, void* y, int64_t n, uav_stream_t stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos, freq_shift) (unet_video.py:173,472): fp32 math, fp16 out */
+uav_status_t uav_timestep_embedding(const float* t, int64_t B, int64_t dim, int flip_sin_to_cos,
+                                    float freq_shift, void* out, uav_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * sampler: run on the reference's own "b c t h w" latents; dtype = UAV_F16 replays torch's
+ * per-op fp16 rounding exactly, UAV_F32 is plain fp32.
+ * ------------------------------------------------------------------------------------------- */
+/* out = uncond + g * (text - uncond); pred2 = [uncond | text], n = elements of one half
+ * (pipeline_upscale_a_video.py:644-645) */
+uav_status_t uav_cfg_combine(const void* pred2, void* out, int64_t n, float guidance_scale,
+                             int dtype, uav_stream_t stream);
+/* dst[:, :, t0+k] = covered(k) ? dst*0.5 + src[:, :, k]*0.5 : src[:, :, k]
+ * (pipeline_upscale_a_video.py:630-634); tensors (outer, T, hw) / (outer, Tw, hw) */
+uav_status_t uav_window_blend(void* dst, int64_t T, const void* src, int64_t Tw, int64_t t0,
+                              uint32_t covered_mask, int64_t outer, int64_t hw, int dtype,
+                              uav_stream_t stream);
+/* DDIMScheduler.step_v0 (scheduling_ddim.py:383-433); pred_type 0 epsilon, 1 sample, 2 v_prediction */
+uav_status_t uav_ddim_step_v0(const void* model_output, const void* sample, void* x0, int64_t n,
+                              int pred_type, float sqrt_alpha, float sqrt_beta, int clip,
+                              float clip_range, int dtype, uav_stream_t stream);
+/* DDIMScheduler.step_vt (scheduling_ddim.py:436-520); dir_coef = (1 - a_prev - std^2)^0.5 */
+uav_status_t uav_ddim_step_vt(const void* x0, const void* model_output, const void* sample,
+                              void* prev, int64_t n, int pred_type, float sqrt_alpha,
+                              float sqrt_beta, float sqrt_alpha_prev, float dir_coef, int clip,
+                              float clip_range, float std_dev, const void* noise, int dtype,
+                              uav_stream_t stream);
+/* add_noise (scheduling_ddim.py:524-545 / diffusers DDPMScheduler.add_noise) */
+uav_status_t uav_add_noise(const void* x, const void* noise, void* out, int64_t n,
+                           float sqrt_alpha, float sqrt_one_minus_alpha, int dtype,
+                           uav_stream_t stream);
+/* one frame update of Propagation.forward, learnable=False (propagation_module.py:234-254):
+ * fbConsistencyCheck mask + flow_warp(nearest|bilinear) + fuse + select, for C planes of H x W.
+ * cs_* = channel (plane) strides in elements.  half_grid_sample: see csrc/sampler.cu. */
+uav_status_t uav_propagate_step(const void* feat_prop, const void* feat_cur, const void* flow_prop,
+                                const void* flow_check, void* out, int64_t C, int64_t H, int64_t W,
+                                int64_t cs_prop, int64_t cs_cur, int64_t cs_out,
+                                int64_t cs_flow_prop, int64_t cs_flow_check, int nearest, int fuse,
+                                float fuse_scale, float alpha1, float alpha2, int half_grid_sample,
+                                int dtype, uav_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

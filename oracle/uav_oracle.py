@@ -129,7 +129,7 @@ def cross_attention(sd: SD, p: str, x, ctx, heads: int):
     v = linear(sd, p + ".to_v", src)
     d = q.shape[-1] // heads
     q, k, v = _heads_to_batch(q, heads), _heads_to_batch(k, heads), _heads_to_batch(v, heads)
-    scores = torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1], dtype=q.dtype), q, k.transpose(-1, -2),
+    scores = torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1], dtype=q.dtype, device=q.device), q, k.transpose(-1, -2),
                            beta=0, alpha=d ** -0.5)
     probs = scores.softmax(dim=-1)
     o = _batch_to_heads(torch.bmm(probs, v), heads)
@@ -151,13 +151,13 @@ def rel_pos_bias(sd: SD, p: str, n: int, num_buckets: int = 32, max_distance: in
     large = torch.min(large, torch.full_like(large, nb - 1))
     bucket = ret + torch.where(is_small, a, large)
     emb = sd[p + ".relative_attention_bias.weight"]  # (num_buckets, heads)
-    return emb[bucket].permute(2, 0, 1)
+    return emb[bucket.to(emb.device)].permute(2, 0, 1)
 
 
 def rotary(freqs, t):
     """rotary-embedding-torch 0.2.3 rotate_queries_or_keys, seq_dim=-2."""
     n = t.shape[-2]
-    ang = torch.arange(n, dtype=freqs.dtype)[:, None] * freqs[None, :]
+    ang = torch.arange(n, dtype=freqs.dtype, device=freqs.device)[:, None] * freqs[None, :]
     ang = torch.repeat_interleave(ang, 2, dim=-1)
     rot = ang.shape[-1]
     tl, tr = t[..., :rot], t[..., rot:]
@@ -250,7 +250,7 @@ def temporal_module3d(sd: SD, p: str, x, temb):
 def timestep_embedding(t, dim: int, flip_sin_to_cos: bool, freq_shift: float):
     """diffusers get_timestep_embedding."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / (half - freq_shift)
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     emb = torch.cat([emb.sin(), emb.cos()], dim=-1)
     if flip_sin_to_cos:
@@ -275,11 +275,11 @@ def unet_forward(sd: SD, cfg: dict, sample, timestep, low_res, encoder_hidden_st
     forward_size = any(s % (2 ** n_up) != 0 for s in sample.shape[-2:])
 
     t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
-    t = t.reshape(-1).expand(sample.shape[0])
+    t = t.to(sample.device).reshape(-1).expand(sample.shape[0])
     t_emb = timestep_embedding(t, boc[0], cfg.get("flip_sin_to_cos", True), cfg.get("freq_shift", 0)).to(dtype)
     emb = linear(sd, "time_embedding.linear_2", F.silu(linear(sd, "time_embedding.linear_1", t_emb)))
     if _has(sd, "class_embedding.weight"):
-        emb = emb + sd["class_embedding.weight"][class_labels].to(dtype)
+        emb = emb + sd["class_embedding.weight"][class_labels.to(sample.device)].to(dtype)
 
     x = inflated_conv(sd, "conv_in", sample)
     skips = [x]
@@ -467,7 +467,8 @@ class DDIM:
         return a_prev ** 0.5 * x0 + direction
 
     def add_noise(self, x, noise, timesteps):
-        ac = self.alphas_cumprod.to(dtype=x.dtype)
+        ac = self.alphas_cumprod.to(device=x.device, dtype=x.dtype)
+        timesteps = timesteps.to(x.device)
         a = (ac[timesteps] ** 0.5).flatten()
         s = ((1 - ac[timesteps]) ** 0.5).flatten()
         while a.dim() < x.dim():

@@ -40,11 +40,29 @@ _PROTOS = {
     "uav_conv2d": [P, I64, I64, I64, I64, I64, P, I64, I32, I32, I32, P, EP, P],
     "uav_conv_temporal": [P, I64, I64, I64, I64, I64, P, I64, I32, P, EP, P],
     "uav_conv3d": [P, I64, I64, I64, I64, I64, I64, P, I64, P, EP, P],
+    "uav_groupnorm_silu": [P, I64, I64, I64, I64, I32, P, P, F32, I32, P, I64, P, C.c_size_t, P],
+    "uav_layernorm": [P, I64, I64, I64, P, P, F32, P, I64, P],
+    "uav_attention": [P, P, P, P, I64, I32, I32, I64, I64, I64, I64, I64, I64, I64, F32, P],
+    "uav_temporal_attention": [P, P, P, P, I64, I64, I64, I32, I32, I64, I64, I64, I64, F32, P, P, P],
+    "uav_copy_channels": [P, I64, P, I64, I64, I64, P],
+    "uav_upsample_nearest": [P, I64, I64, I64, I64, I64, P, I64, I64, I64, P],
+    "uav_planar_to_channels_last": [P, I32, I64, I64, I64, P, I64, I64, F32, P],
+    "uav_channels_last_to_planar": [P, I32, I64, I64, I64, I64, P, I32, I32, P],
+    "uav_silu": [P, P, I64, P],
+    "uav_timestep_embedding": [P, I64, I64, I32, F32, P, P],
+    "uav_cfg_combine": [P, P, I64, F32, I32, P],
+    "uav_window_blend": [P, I64, P, I64, I64, C.c_uint32, I64, I64, I32, P],
+    "uav_ddim_step_v0": [P, P, P, I64, I32, F32, F32, I32, F32, I32, P],
+    "uav_ddim_step_vt": [P, P, P, P, I64, I32, F32, F32, F32, F32, I32, F32, F32, P, I32, P],
+    "uav_add_noise": [P, P, P, I64, F32, F32, I32, P],
+    "uav_propagate_step": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I32, I32, F32, F32, F32,
+                           I32, I32, P],
 }
 _SPECIAL = {
     "uav_version": (C.c_char_p, []),
     "uav_last_error_string": (C.c_char_p, []),
     "uav_launch_count": (C.c_uint64, []),
+    "uav_groupnorm_workspace_bytes": (C.c_size_t, [I64, I32]),
 }
 
 

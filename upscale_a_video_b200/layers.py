@@ -1,0 +1,583 @@
+"""Parameter containers with the reference's module / state-dict names + the channels-last CUDA forward of
+every block on the sampling path.
+
+The classes mirror /root/reference/models_video/{resnet,attention,temporal_module,unet_blocks}.py by NAME and by
+parameter layout (so `load_state_dict(strict=True)` of a reference checkpoint works), but they hold parameters
+only: the arithmetic is in `csrc/` behind the C ABI and is driven by the `forward` methods below on fp16
+channels-last tensors (b, t, h, w, c).  `torch.nn.{Conv2d,Conv3d,Linear,GroupNorm,LayerNorm,Embedding}` are used
+purely as parameter holders (their own forward is never called).
+
+Kernel-ready weights (K-major fp16 conv filters, fused q/k/v matrices, fp32 affine vectors) are packed lazily by
+`Packed` and cached until the parameters change (`_apply` / `load_state_dict`).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------
+# packed weights
+# ------------------------------------------------------------------------------------------------
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class Packed:
+    """kernel-ready views of a module tree's parameters, keyed by parameter name"""
+
+    def __init__(self, root: nn.Module):
+        self.root = root
+        self.cache: Dict[str, torch.Tensor] = {}
+
+    def clear(self):
+        self.cache.clear()
+
+    def conv(self, m: nn.Module):
+        """-> (weight [Cout][taps...][Cin_pad8] fp16, bias fp32 | None)"""
+        key = id(m)
+        if key not in self.cache:
+            w = m.weight.detach()
+            cin = w.shape[1]
+            if w.dim() == 4:
+                wp = w.permute(0, 2, 3, 1)
+            elif w.shape[3] == 1 and w.shape[4] == 1:
+                wp = w[:, :, :, 0, 0].permute(0, 2, 1)
+            else:
+                wp = w.permute(0, 2, 3, 4, 1)
+            if cin % 8:
+                wp = torch.nn.functional.pad(wp, (0, _pad8(cin) - cin))
+            self.cache[key] = (wp.to(torch.float16).contiguous(),
+                               None if m.bias is None else m.bias.detach().float().contiguous())
+        return self.cache[key]
+
+    def linear(self, m: nn.Module):
+        key = id(m)
+        if key not in self.cache:
+            self.cache[key] = (m.weight.detach().to(torch.float16).contiguous(),
+                               None if m.bias is None else m.bias.detach().float().contiguous())
+        return self.cache[key]
+
+    def fused_linear(self, key: str, mods):
+        """row-concatenated weights of several Linear layers sharing one input (q|k|v, k|v, all temb projections)"""
+        if key not in self.cache:
+            w = torch.cat([m.weight.detach().to(torch.float16) for m in mods], dim=0).contiguous()
+            if all(m.bias is None for m in mods):
+                b = None
+            else:
+                b = torch.cat([(m.bias.detach().float() if m.bias is not None else
+                                torch.zeros(m.weight.shape[0], device=w.device)) for m in mods]).contiguous()
+            self.cache[key] = (w, b)
+        return self.cache[key]
+
+    def affine(self, m: nn.Module):
+        key = id(m)
+        if key not in self.cache:
+            self.cache[key] = (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
+        return self.cache[key]
+
+    def tensor(self, key: str, fn):
+        if key not in self.cache:
+            self.cache[key] = fn()
+        return self.cache[key]
+
+
+class PackedModule(nn.Module):
+    """root module mixin: owns the Packed cache and invalidates it when parameters move / change"""
+
+    def _packed(self) -> Packed:
+        pk = self.__dict__.get("_pk")
+        if pk is None:
+            pk = Packed(self)
+            self.__dict__["_pk"] = pk
+        return pk
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        if self.__dict__.get("_pk") is not None:
+            self.__dict__["_pk"].clear()
+        return r
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super().load_state_dict(*args, **kwargs)
+        if self.__dict__.get("_pk") is not None:
+            self.__dict__["_pk"].clear()
+        return r
+
+
+# ------------------------------------------------------------------------------------------------
+# forward context
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    """per-forward state: packed weights, the batched time-embedding projections, cached prompt K/V"""
+
+    def __init__(self, pk: Packed):
+        self.pk = pk
+        self.temb_all: Optional[torch.Tensor] = None    # (B, sum Cout) fp16
+        self.temb_slices: Dict[int, tuple] = {}          # id(resnet) -> (col0, col1)
+        self.ctx_kv: Optional[torch.Tensor] = None       # (B*77, sum 2C) fp16
+        self.ctx_slices: Dict[int, tuple] = {}           # id(attn) -> (col0, C)
+        self.ctx_len = 0
+        self.rot: Optional[torch.Tensor] = None
+        self.rel_bias: Dict[int, torch.Tensor] = {}
+
+    def temb(self, resnet):
+        if self.temb_all is None or id(resnet) not in self.temb_slices:
+            return None
+        c0, c1 = self.temb_slices[id(resnet)]
+        return self.temb_all[:, c0:c1]
+
+
+# ------------------------------------------------------------------------------------------------
+# resnet.py
+# ------------------------------------------------------------------------------------------------
+class InflatedConv3d(nn.Conv2d):
+    """resnet.py:94-101 — parameter holder; executed by `ops.conv2d` on (b, t, h, w, c)"""
+
+    def run(self, c: Ctx, x, **epi):
+        w, b = c.pk.conv(self)
+        stride = self.stride[0]
+        if stride == 2:
+            pad_mode = 0 if self.padding[0] == 1 else 1
+            H, W = x.shape[-3], x.shape[-2]
+            if H % 2 or W % 2:  # zero row/col == the conv's own zero padding (exact)
+                xp = torch.zeros(*x.shape[:-3], H + H % 2, W + W % 2, x.shape[-1], dtype=x.dtype, device=x.device)
+                xp[..., :H, :W, :].copy_(x)  # strided plumbing copy (only for odd sizes, e.g. 45 -> 23 at 180x320)
+                x = xp
+            return ops.conv2d(x, w, b, stride=2, pad_mode=pad_mode, **epi)
+        return ops.conv2d(x, w, b, **epi)
+
+
+def _gn(c: Ctx, norm: nn.GroupNorm, x, silu: bool, n_outer: int):
+    g, b = c.pk.affine(norm)
+    return ops.group_norm(x, g, b, norm.num_groups, norm.eps, silu=silu, n_outer=n_outer)
+
+
+class ResnetBlock3D(nn.Module):
+    """resnet.py:200-294"""
+
+    def __init__(self, *, in_channels, out_channels=None, temb_channels=512, groups=32, groups_out=None, eps=1e-6,
+                 output_scale_factor=1.0, **_):
+        super().__init__()
+        out_channels = in_channels if out_channels is None else out_channels
+        groups_out = groups if groups_out is None else groups_out
+        self.in_channels, self.out_channels = in_channels, out_channels
+        assert output_scale_factor == 1.0, "output_scale_factor != 1 is not used by any shipped config"
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = InflatedConv3d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(groups_out, out_channels, eps=eps, affine=True)
+        self.conv2 = InflatedConv3d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.conv_shortcut = (InflatedConv3d(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
+                              if in_channels != out_channels else None)
+
+    def _convs(self, c, h, which, **epi):
+        return getattr(self, which).run(c, h, **epi)
+
+    def forward(self, c: Ctx, x):
+        B = x.shape[0]
+        thw = x.shape[1] * x.shape[2] * x.shape[3]
+        h = _gn(c, self.norm1, x, True, B)
+        temb = c.temb(self) if self.time_emb_proj is not None else None
+        h = self._convs(c, h, "conv1", rowvec=temb, rows_per_vec=thw)
+        h = _gn(c, self.norm2, h, True, B)
+        xs = x if self.conv_shortcut is None else self._convs(c, x, "conv_shortcut")
+        return self._convs(c, h, "conv2", residual=xs)
+
+
+class TemporalConv(nn.Conv3d):
+    """nn.Conv3d (k,1,1) / (1,1,1) / (3,3,3) parameter holder (resnet.py:332,348,361,461)"""
+
+    def run(self, c: Ctx, x, **epi):
+        w, b = c.pk.conv(self)
+        if w.dim() == 3:
+            return ops.conv_temporal(x, w, b, **epi)
+        epi.pop("rowvec", None)
+        epi.pop("rows_per_vec", None)
+        return ops.conv3d(x, w, b, **epi)
+
+
+class ResnetBlock3DCNN(ResnetBlock3D):
+    """resnet.py:297-393 — temporal (k,1,1) convolutions"""
+
+    def __init__(self, *, in_channels, out_channels=None, kernel=(3, 1, 1), temb_channels=512, groups=32, eps=1e-6, **_):
+        nn.Module.__init__(self)
+        out_channels = in_channels if out_channels is None else out_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        pad = tuple((k - 1) // 2 for k in kernel)
+        self.conv1 = TemporalConv(in_channels, out_channels, kernel_size=kernel, stride=(1, 1, 1), padding=pad)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps, affine=True)
+        self.conv2 = TemporalConv(out_channels, out_channels, kernel_size=(3, 1, 1), stride=(1, 1, 1), padding=(1, 0, 0))
+        self.conv_shortcut = (TemporalConv(in_channels, out_channels, kernel_size=(1, 1, 1))
+                              if in_channels != out_channels else None)
+
+
+class ResnetBlock3D_plus(ResnetBlock3D):
+    """resnet.py:396-500 — ResnetBlock3D + GN -> SiLU -> zero-init Conv3d 3x3x3 residual (video VAE)"""
+
+    def __init__(self, *, in_channels, out_channels=None, temb_channels=512, groups=32, groups_out=None, eps=1e-6, **kw):
+        super().__init__(in_channels=in_channels, out_channels=out_channels, temb_channels=temb_channels, groups=groups,
+                         groups_out=groups_out, eps=eps)
+        go = groups if groups_out is None else groups_out
+        self.norm_3d = nn.GroupNorm(go, self.out_channels, eps=eps, affine=True)
+        self.conv_3d = TemporalConv(self.out_channels, self.out_channels, kernel_size=(3, 3, 3), stride=(1, 1, 1),
+                                    padding=(1, 1, 1))
+        nn.init.zeros_(self.conv_3d.weight)
+        nn.init.zeros_(self.conv_3d.bias)
+
+    def forward(self, c: Ctx, x):
+        out = super().forward(c, x)
+        h = _gn(c, self.norm_3d, out, True, x.shape[0])
+        return self.conv_3d.run(c, h, residual=out)
+
+
+class Upsample3D(nn.Module):
+    """resnet.py:104-158"""
+
+    def __init__(self, channels, use_conv=False, out_channels=None, **_):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.conv = InflatedConv3d(channels, self.out_channels, 3, padding=1) if use_conv else None
+
+    def forward(self, c: Ctx, x, output_size=None):
+        assert x.shape[-1] == self.channels
+        x = ops.upsample_nearest(x, None if output_size is None else tuple(output_size[-2:]))
+        return x if self.conv is None else self.conv.run(c, x)
+
+
+class Downsample3D(nn.Module):
+    """resnet.py:161-197 (use_conv=True; name='op')"""
+
+    def __init__(self, channels, use_conv=True, out_channels=None, padding=1, name="conv"):
+        super().__init__()
+        assert use_conv
+        self.channels, self.out_channels, self.padding = channels, out_channels or channels, padding
+        self.conv = InflatedConv3d(channels, self.out_channels, 3, stride=2, padding=padding)
+
+    def forward(self, c: Ctx, x):
+        assert x.shape[-1] == self.channels
+        return self.conv.run(c, x)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention.py
+# ------------------------------------------------------------------------------------------------
+class CrossAttention(nn.Module):
+    """attention.py:44-238 parameter holder"""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, bias=False):
+        super().__init__()
+        inner = dim_head * heads
+        self.is_cross = cross_attention_dim is not None
+        kv_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.heads, self.dim_head, self.scale = heads, dim_head, dim_head ** -0.5
+        self._use_memory_efficient_attention_xformers = False
+        self.to_q = nn.Linear(query_dim, inner, bias=bias)
+        self.to_k = nn.Linear(kv_dim, inner, bias=bias)
+        self.to_v = nn.Linear(kv_dim, inner, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+    def forward(self, c: Ctx, n, hs, frames: int):
+        """n: normalised tokens (B, T, HW, C); hs: residual stream; returns to_out(attn(n)) + hs"""
+        B, T, HW, C = n.shape
+        if self.is_cross:
+            wq, bq = c.pk.linear(self.to_q)
+            q = ops.linear(n, wq, bq).view(B * T, HW, C)
+            c0, cc = c.ctx_slices[id(self)]
+            kv = c.ctx_kv.view(B, c.ctx_len, -1)
+            k, v = kv[:, :, c0:c0 + cc], kv[:, :, c0 + cc:c0 + 2 * cc]
+            o = ops.attention(q, k, v, self.heads, kv_batch_div=T)
+        else:
+            w, b = c.pk.fused_linear(f"qkv{id(self)}", [self.to_q, self.to_k, self.to_v])
+            qkv = ops.linear(n, w, b).view(B * T, HW, 3 * C)
+            o = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.heads)
+        wo, bo = c.pk.linear(self.to_out[0])
+        return ops.linear(o.view(B, T, HW, C), wo, bo, residual=hs)
+
+
+class RotaryEmbedding(nn.Module):
+    """rotary-embedding-torch 0.2.3 parameter holder (unet_video.py:203): `freqs` = theta^(-2j/dim)"""
+
+    def __init__(self, dim, theta=10000):
+        super().__init__()
+        self.freqs = nn.Parameter(1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)), requires_grad=False)
+
+    def table(self, n: int) -> torch.Tensor:
+        """(n, dim/2, 2) fp32: cos/sin of position * freq"""
+        f = self.freqs.detach().float()
+        ang = torch.arange(n, device=f.device, dtype=torch.float32)[:, None] * f[None, :]
+        return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+
+
+class RelativePositionBias(nn.Module):
+    """attention.py:735-773"""
+
+    def __init__(self, heads=8, num_buckets=32, max_distance=128):
+        super().__init__()
+        self.num_buckets, self.max_distance = num_buckets, max_distance
+        self.relative_attention_bias = nn.Embedding(num_buckets, heads)
+
+    def table(self, n: int) -> torch.Tensor:
+        """(heads, n, n) fp32 — host-side index math (attention.py:747-773), one tiny gather on device"""
+        import math
+        q = torch.arange(n)
+        rel = q[None, :] - q[:, None]
+        nb = self.num_buckets // 2
+        neg = -rel
+        ret = (neg < 0).long() * nb
+        a = neg.abs()
+        max_exact = nb // 2
+        large = max_exact + (torch.log(a.float().clamp(min=1) / max_exact) / math.log(self.max_distance / max_exact)
+                             * (nb - max_exact)).long()
+        large = torch.min(large, torch.full_like(large, nb - 1))
+        bucket = ret + torch.where(a < max_exact, a, large)
+        w = self.relative_attention_bias.weight.detach().float()
+        return w[bucket.to(w.device)].permute(2, 0, 1).contiguous()
+
+
+class TemporalAttention(CrossAttention):
+    """attention.py:626-733"""
+
+    def __init__(self, query_dim, heads=8, dim_head=64, bias=False, rotary_emb=None):
+        super().__init__(query_dim, None, heads, dim_head, bias)
+        self.time_rel_pos_bias = RelativePositionBias(heads=heads, max_distance=32)
+        self.rotary_emb = rotary_emb  # shared module: the reference state dict carries `...rotary_emb.freqs` per site
+
+    def forward(self, c: Ctx, n, hs, frames: int):
+        B, T, HW, C = n.shape
+        w, b = c.pk.fused_linear(f"qkv{id(self)}", [self.to_q, self.to_k, self.to_v])
+        qkv = ops.linear(n, w, b)
+        bias = c.pk.tensor(f"relbias{id(self)}_{T}", lambda: self.time_rel_pos_bias.table(T))
+        o = ops.temporal_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.heads, c.rot, bias)
+        wo, bo = c.pk.linear(self.to_out[0])
+        return ops.linear(o, wo, bo, residual=hs)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """diffusers FeedForward(activation_fn='geglu') parameter holder (attention.py:18,493)"""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+    def forward(self, c: Ctx, n, hs):
+        w1, b1 = c.pk.linear(self.net[0].proj)
+        g = ops.linear(n, w1, b1, act=ops.ACT_GEGLU)
+        w2, b2 = c.pk.linear(self.net[2])
+        return ops.linear(g, w2, b2, residual=hs)
+
+
+class BasicTransformerBlock(nn.Module):
+    """attention.py:414-564"""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, cross_attention_dim=None, attention_bias=False,
+                 only_cross_attention=False, rotary_emb=None):
+        super().__init__()
+        self.only_cross_attention = only_cross_attention
+        self.attn1 = CrossAttention(dim, cross_attention_dim if only_cross_attention else None, num_attention_heads,
+                                    attention_head_dim, attention_bias)
+        self.norm1 = nn.LayerNorm(dim)
+        if cross_attention_dim is not None:
+            self.attn2 = CrossAttention(dim, cross_attention_dim, num_attention_heads, attention_head_dim, attention_bias)
+            self.norm2 = nn.LayerNorm(dim)
+        else:
+            self.attn2, self.norm2 = None, None
+        self.attn_temporal = TemporalAttention(dim, num_attention_heads, attention_head_dim, attention_bias, rotary_emb)
+        nn.init.zeros_(self.attn_temporal.to_out[0].weight.data)
+        self.norm_temporal = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+        self.norm3 = nn.LayerNorm(dim)
+
+    def _ln(self, c, m, x):
+        g, b = c.pk.affine(m)
+        return ops.layer_norm(x, g, b, m.eps)
+
+    def forward(self, c: Ctx, hs):
+        T = hs.shape[1]
+        hs = self.attn1(c, self._ln(c, self.norm1, hs), hs, T)
+        if self.attn2 is not None:
+            hs = self.attn2(c, self._ln(c, self.norm2, hs), hs, T)
+        hs = self.attn_temporal(c, self._ln(c, self.norm_temporal, hs), hs, T)
+        return self.ff(c, self._ln(c, self.norm3, hs), hs)
+
+
+class Transformer3DModel(nn.Module):
+    """attention.py:292-411 (use_linear_projection=True)"""
+
+    def __init__(self, num_attention_heads=16, attention_head_dim=88, in_channels=None, num_layers=1,
+                 norm_num_groups=32, cross_attention_dim=None, use_linear_projection=False, only_cross_attention=False,
+                 rotary_emb=None, **_):
+        super().__init__()
+        assert use_linear_projection, "only use_linear_projection=True (shipped config) is implemented"
+        inner = num_attention_heads * attention_head_dim
+        self.in_channels = in_channels
+        self.resblock_temporal = ResnetBlock3DCNN(in_channels=in_channels, kernel=(3, 1, 1), temb_channels=None)
+        self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner, num_attention_heads, attention_head_dim, cross_attention_dim=cross_attention_dim,
+                                  only_cross_attention=only_cross_attention, rotary_emb=rotary_emb)
+            for _ in range(num_layers)])
+        self.proj_out = nn.Linear(in_channels, inner)
+
+    def forward(self, c: Ctx, x):
+        B, T, H, W, C = x.shape
+        x = self.resblock_temporal(c, x)
+        hs = _gn(c, self.norm, x, False, B * T)
+        w, b = c.pk.linear(self.proj_in)
+        hs = ops.linear(hs.view(B, T, H * W, C), w, b)
+        for blk in self.transformer_blocks:
+            hs = blk(c, hs)
+        w, b = c.pk.linear(self.proj_out)
+        return ops.linear(hs, w, b, residual=x.view(B, T, H * W, C)).view(B, T, H, W, C)
+
+
+# ------------------------------------------------------------------------------------------------
+# temporal_module.py
+# ------------------------------------------------------------------------------------------------
+class TemporalModule3D(nn.Module):
+    """temporal_module.py:98-194 with attention_block_types=("","") (shipped config): no attention inside"""
+
+    def __init__(self, in_channels=None, out_channels=None, temb_channels=512, attention_block_types=("", ""), **_):
+        super().__init__()
+        if tuple(attention_block_types) != ("", ""):
+            raise NotImplementedError("TemporalTransformer3DModel is dead under the shipped config and out of scope")
+        self.resblocks_3d_temporal = ResnetBlock3DCNN(in_channels=in_channels, out_channels=in_channels, kernel=(5, 1, 1),
+                                                      temb_channels=temb_channels)
+        self.resblocks_3d_spatial = ResnetBlock3D(in_channels=in_channels, out_channels=in_channels,
+                                                  temb_channels=temb_channels, groups=32, groups_out=32)
+        self.shift_conv = InflatedConv3d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        nn.init.zeros_(self.shift_conv.weight)
+        nn.init.zeros_(self.shift_conv.bias)
+
+    def forward(self, c: Ctx, x):
+        h = self.resblocks_3d_temporal(c, x)
+        h = self.resblocks_3d_spatial(c, h)
+        return self.shift_conv.run(c, h, residual=x)
+
+
+class EmptyTemporalModule3D(nn.Module):
+    def forward(self, c: Ctx, x):
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+# unet_blocks.py (UNet side)
+# ------------------------------------------------------------------------------------------------
+def _t3d(heads, channels, cross_dim, groups, only_cross, rotary):
+    return Transformer3DModel(heads, channels // heads, in_channels=channels, num_layers=1, cross_attention_dim=cross_dim,
+                              norm_num_groups=groups, use_linear_projection=True, only_cross_attention=only_cross,
+                              rotary_emb=rotary)
+
+
+class DownBlock3D(nn.Module):
+    """unet_blocks.py:415-487"""
+    has_cross_attention = False
+
+    def __init__(self, in_channels, out_channels, temb_channels, num_layers=1, resnet_eps=1e-6, resnet_groups=32,
+                 add_downsample=True, downsample_padding=1, **_):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlock3D(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                          temb_channels=temb_channels, eps=resnet_eps, groups=resnet_groups) for i in range(num_layers)])
+        self.attentions = None
+        self.downsamplers = (nn.ModuleList([Downsample3D(out_channels, True, out_channels, downsample_padding, "op")])
+                             if add_downsample else None)
+
+    def forward(self, c: Ctx, x):
+        outs = []
+        for i, r in enumerate(self.resnets):
+            x = r(c, x)
+            if self.attentions is not None:
+                x = self.attentions[i](c, x)
+            outs.append(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](c, x)
+            outs.append(x)
+        return x, outs
+
+
+class CrossAttnDownBlock3D(DownBlock3D):
+    """unet_blocks.py:270-412"""
+    has_cross_attention = True
+
+    def __init__(self, in_channels, out_channels, temb_channels, num_layers=1, resnet_eps=1e-6, resnet_groups=32,
+                 attn_num_head_channels=1, cross_attention_dim=1280, add_downsample=True, downsample_padding=1,
+                 only_cross_attention=False, rotary_emb=None, **_):
+        super().__init__(in_channels, out_channels, temb_channels, num_layers, resnet_eps, resnet_groups, add_downsample,
+                         downsample_padding)
+        self.attentions = nn.ModuleList([_t3d(attn_num_head_channels, out_channels, cross_attention_dim, resnet_groups,
+                                              only_cross_attention, rotary_emb) for _ in range(num_layers)])
+
+
+class UNetMidBlock3DCrossAttn(nn.Module):
+    """unet_blocks.py:180-267"""
+    has_cross_attention = True
+
+    def __init__(self, in_channels, temb_channels, resnet_eps=1e-6, resnet_groups=32, attn_num_head_channels=1,
+                 cross_attention_dim=1280, rotary_emb=None, **_):
+        super().__init__()
+        mk = lambda: ResnetBlock3D(in_channels=in_channels, out_channels=in_channels, temb_channels=temb_channels,  # noqa
+                                   eps=resnet_eps, groups=resnet_groups)
+        self.attentions = nn.ModuleList([_t3d(attn_num_head_channels, in_channels, cross_attention_dim, resnet_groups,
+                                              False, rotary_emb)])
+        self.resnets = nn.ModuleList([mk(), mk()])
+
+    def forward(self, c: Ctx, x):
+        x = self.resnets[0](c, x)
+        x = self.attentions[0](c, x)
+        return self.resnets[1](c, x)
+
+
+class UpBlock3D(nn.Module):
+    """unet_blocks.py:588-660"""
+    has_cross_attention = False
+
+    def __init__(self, in_channels, prev_output_channel, out_channels, temb_channels, num_layers=1, resnet_eps=1e-6,
+                 resnet_groups=32, add_upsample=True, **_):
+        super().__init__()
+        res = []
+        for i in range(num_layers):
+            skip = in_channels if i == num_layers - 1 else out_channels
+            rin = prev_output_channel if i == 0 else out_channels
+            res.append(ResnetBlock3D(in_channels=rin + skip, out_channels=out_channels, temb_channels=temb_channels,
+                                     eps=resnet_eps, groups=resnet_groups))
+        self.resnets = nn.ModuleList(res)
+        self.attentions = None
+        self.upsamplers = nn.ModuleList([Upsample3D(out_channels, True, out_channels)]) if add_upsample else None
+
+    def forward(self, c: Ctx, x, skips, upsample_size=None):
+        for i, r in enumerate(self.resnets):
+            x = ops.concat_channels(x, skips[-1 - i])
+            x = r(c, x)
+            if self.attentions is not None:
+                x = self.attentions[i](c, x)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](c, x, upsample_size)
+        return x
+
+
+class CrossAttnUpBlock3D(UpBlock3D):
+    """unet_blocks.py:490-585"""
+    has_cross_attention = True
+
+    def __init__(self, in_channels, out_channels, prev_output_channel, temb_channels, num_layers=1, resnet_eps=1e-6,
+                 resnet_groups=32, attn_num_head_channels=1, cross_attention_dim=1280, add_upsample=True,
+                 only_cross_attention=False, rotary_emb=None, **_):
+        super().__init__(in_channels, prev_output_channel, out_channels, temb_channels, num_layers, resnet_eps,
+                         resnet_groups, add_upsample)
+        self.attentions = nn.ModuleList([_t3d(attn_num_head_channels, out_channels, cross_attention_dim, resnet_groups,
+                                              only_cross_attention, rotary_emb) for _ in range(num_layers)])

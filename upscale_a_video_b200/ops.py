@@ -128,3 +128,244 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=No
     _lib.check(lib.uav_conv3d(x.data_ptr(), B, T, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout,
                               out.data_ptr(), C.byref(e), _stream()), "uav_conv3d")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------
+_gn_ws = {}
+
+
+def _gn_workspace(device, nbytes):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _gn_ws[key] = ws
+    return ws
+
+
+def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *, silu: bool,
+               n_outer: int, out: Optional[torch.Tensor] = None):
+    """x: channels-last (..., C) fp16; statistics per (outer index, group) where the leading `n_outer` slabs of
+    x.numel()/C/n_outer pixels each are normalised independently (5-D GN: n_outer=b; per-frame GN: n_outer=b*t)."""
+    assert x.dtype == torch.float16 and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    C = x.shape[-1]
+    total_pix = x.numel() // C
+    assert total_pix % n_outer == 0
+    pixels = total_pix // n_outer
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lib = _lib.load()
+    nbytes = lib.uav_groupnorm_workspace_bytes(n_outer, groups)
+    ws = _gn_workspace(x.device, nbytes)
+    _lib.check(lib.uav_groupnorm_silu(x.data_ptr(), n_outer, pixels, C, _pixel_ld(x), groups, gamma.data_ptr(),
+                                      beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), _pixel_ld(out),
+                                      ws.data_ptr(), ws.numel(), _stream()), "uav_groupnorm_silu")
+    return out
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, out=None):
+    assert x.dtype == torch.float16 and gamma.dtype == torch.float32
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_layernorm(x.data_ptr(), rows, C, _pixel_ld(x), gamma.data_ptr(), beta.data_ptr(), eps,
+                                 out.data_ptr(), _pixel_ld(out), _stream()), "uav_layernorm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attention(q, k, v, heads: int, *, kv_batch_div: int = 1, scale: Optional[float] = None, out=None):
+    """q: (batch, nq, heads*d) fp16 (may be a column slice of a fused qkv buffer); k, v: (batch/kv_batch_div, nk, heads*d)."""
+    batch, nq, C = q.shape
+    d = C // heads
+    nk = k.shape[1]
+    assert k.shape[0] * kv_batch_div == batch and v.shape[:2] == k.shape[:2]
+    if out is None:
+        out = torch.empty(batch, nq, C, dtype=torch.float16, device=q.device)
+    if scale is None:
+        scale = d ** -0.5
+    for t in (q, k, v, out):
+        assert t.dtype == torch.float16 and t.stride(-1) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    lib = _lib.load()
+    _lib.check(lib.uav_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, d, nq, nk,
+                                 q.stride(1), k.stride(1), v.stride(1), out.stride(1), kv_batch_div, scale,
+                                 _stream()), "uav_attention")
+    return out
+
+
+def temporal_attention(q, k, v, heads: int, rot: torch.Tensor, bias: torch.Tensor, *, out=None):
+    """q, k, v: (B, F, HW, heads*d) fp16 (column slices allowed); rot: (F,16,2) fp32 cos/sin; bias: (heads,F,F) fp32."""
+    B, F, HW, C = q.shape
+    d = C // heads
+    if out is None:
+        out = torch.empty(B, F, HW, C, dtype=torch.float16, device=q.device)
+    assert rot.dtype == torch.float32 and rot.is_contiguous() and tuple(rot.shape) == (F, 16, 2)
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and tuple(bias.shape) == (heads, F, F)
+    lib = _lib.load()
+    _lib.check(lib.uav_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, F, HW, heads, d,
+                                          _pixel_ld(q), _pixel_ld(k), _pixel_ld(v), _pixel_ld(out), d ** -0.5,
+                                          rot.data_ptr(), bias.data_ptr(), _stream()), "uav_temporal_attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# data movement
+# ------------------------------------------------------------------------------------------------
+def copy_channels(src: torch.Tensor, dst: torch.Tensor):
+    """dst[..., :C] = src (both channels-last views with the same pixel count)"""
+    C = src.shape[-1]
+    assert dst.shape[-1] == C and src.numel() == dst.numel()
+    lib = _lib.load()
+    _lib.check(lib.uav_copy_channels(src.data_ptr(), _pixel_ld(src), dst.data_ptr(), _pixel_ld(dst), C,
+                                     src.numel() // C, _stream()), "uav_copy_channels")
+    return dst
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor):
+    """torch.cat([a, b], dim=channel) for channels-last tensors"""
+    out = torch.empty(*a.shape[:-1], a.shape[-1] + b.shape[-1], dtype=a.dtype, device=a.device)
+    copy_channels(a, out[..., : a.shape[-1]])
+    copy_channels(b, out[..., a.shape[-1]:])
+    return out
+
+
+def upsample_nearest(x: torch.Tensor, size=None):
+    """x: (..., H, W, C); nearest x2 in H, W (or to explicit (Ho, Wo))"""
+    *lead, H, W, C = x.shape
+    Ho, Wo = (2 * H, 2 * W) if size is None else size
+    NB = 1
+    for d in lead:
+        NB *= d
+    out = torch.empty(*lead, Ho, Wo, C, dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_upsample_nearest(x.data_ptr(), _pixel_ld(x), NB, H, W, C, out.data_ptr(), _pixel_ld(out), Ho, Wo,
+                                        _stream()), "uav_upsample_nearest")
+    return out
+
+
+def planar_to_channels_last(src: torch.Tensor, dst: torch.Tensor, c_off: int = 0, scale: float = 1.0):
+    """src: (B, C, T, H, W) fp16/fp32 contiguous -> dst[(B,T,H,W), c_off:c_off+C] (fp16 channels-last)"""
+    assert src.is_contiguous() and dst.dtype == torch.float16
+    B, Cc = src.shape[:2]
+    thw = src.numel() // (B * Cc)
+    lib = _lib.load()
+    _lib.check(lib.uav_planar_to_channels_last(src.data_ptr(), F16 if src.dtype == torch.float16 else F32, B, Cc, thw,
+                                               dst.data_ptr(), _pixel_ld(dst), c_off, scale, _stream()),
+               "uav_planar_to_channels_last")
+    return dst
+
+
+def channels_last_to_planar(src: torch.Tensor, C: int, out_dtype, clamp: bool = False):
+    """src: (B, T, H, W, ld) channels-last (fp16/fp32) -> (B, C, T, H, W) of out_dtype"""
+    B, T, H, W, _ = src.shape
+    out = torch.empty(B, C, T, H, W, dtype=out_dtype, device=src.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_channels_last_to_planar(src.data_ptr(), F16 if src.dtype == torch.float16 else F32,
+                                               _pixel_ld(src), B, C, T * H * W, out.data_ptr(),
+                                               F16 if out_dtype == torch.float16 else F32, 1 if clamp else 0,
+                                               _stream()), "uav_channels_last_to_planar")
+    return out
+
+
+def silu(x: torch.Tensor):
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    _lib.check(lib.uav_silu(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "uav_silu")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float):
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty(t.shape[0], dim, dtype=torch.float16, device=t.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_timestep_embedding(t.data_ptr(), t.shape[0], dim, 1 if flip_sin_to_cos else 0, freq_shift,
+                                          out.data_ptr(), _stream()), "uav_timestep_embedding")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler (operate on the reference's b c t h w latents)
+# ------------------------------------------------------------------------------------------------
+def _dt(x):
+    assert x.dtype in (torch.float16, torch.float32) and x.is_contiguous() and x.is_cuda
+    return F16 if x.dtype == torch.float16 else F32
+
+
+def cfg_combine(pred2: torch.Tensor, guidance_scale: float):
+    assert pred2.shape[0] % 2 == 0
+    out = torch.empty(pred2.shape[0] // 2, *pred2.shape[1:], dtype=pred2.dtype, device=pred2.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_cfg_combine(pred2.data_ptr(), out.data_ptr(), out.numel(), guidance_scale, _dt(pred2), _stream()),
+               "uav_cfg_combine")
+    return out
+
+
+def window_blend(dst: torch.Tensor, src: torch.Tensor, t0: int, covered_mask: int):
+    """dst: (B, C, T, H, W); src: (B, C, Tw, H, W)"""
+    B, Cc, T, H, W = dst.shape
+    Tw = src.shape[2]
+    assert src.dtype == dst.dtype
+    lib = _lib.load()
+    _lib.check(lib.uav_window_blend(dst.data_ptr(), T, src.data_ptr(), Tw, t0, covered_mask, B * Cc, H * W, _dt(dst),
+                                    _stream()), "uav_window_blend")
+    _dt(src)
+    return dst
+
+
+def ddim_step_v0(model_output, sample, pred_type: int, sqrt_alpha: float, sqrt_beta: float, clip: bool, clip_range: float):
+    out = torch.empty_like(sample)
+    lib = _lib.load()
+    assert model_output.dtype == sample.dtype
+    _dt(model_output)
+    _lib.check(lib.uav_ddim_step_v0(model_output.data_ptr(), sample.data_ptr(), out.data_ptr(), sample.numel(), pred_type,
+                                    sqrt_alpha, sqrt_beta, 1 if clip else 0, clip_range, _dt(sample), _stream()),
+               "uav_ddim_step_v0")
+    return out
+
+
+def ddim_step_vt(x0, model_output, sample, pred_type: int, sqrt_alpha, sqrt_beta, sqrt_alpha_prev, dir_coef, clip: bool,
+                 clip_range: float, std_dev: float = 0.0, noise=None):
+    out = torch.empty_like(sample)
+    lib = _lib.load()
+    for t in (x0, model_output):
+        assert t.dtype == sample.dtype
+        _dt(t)
+    _lib.check(lib.uav_ddim_step_vt(x0.data_ptr(), model_output.data_ptr(), sample.data_ptr(), out.data_ptr(),
+                                    sample.numel(), pred_type, sqrt_alpha, sqrt_beta, sqrt_alpha_prev, dir_coef,
+                                    1 if clip else 0, clip_range, std_dev,
+                                    noise.data_ptr() if noise is not None else None, _dt(sample), _stream()),
+               "uav_ddim_step_vt")
+    return out
+
+
+def add_noise(x, noise, sqrt_alpha: float, sqrt_one_minus_alpha: float):
+    out = torch.empty_like(x)
+    assert noise.dtype == x.dtype
+    _dt(noise)
+    lib = _lib.load()
+    _lib.check(lib.uav_add_noise(x.data_ptr(), noise.data_ptr(), out.data_ptr(), x.numel(), sqrt_alpha,
+                                 sqrt_one_minus_alpha, _dt(x), _stream()), "uav_add_noise")
+    return out
+
+
+def propagate_step(feat_prop, feat_cur, flow_prop, flow_check, out, *, nearest: bool, fuse: bool, fuse_scale: float,
+                   alpha1: float, alpha2: float, half_grid_sample: bool):
+    """all tensors are (C|2, H, W) views with contiguous planes (stride(-1)==1, stride(-2)==W)"""
+    Cc, H, W = feat_prop.shape
+    for t in (feat_prop, feat_cur, flow_prop, flow_check, out):
+        assert t.stride(-1) == 1 and t.stride(-2) == W and t.dtype == feat_prop.dtype and t.is_cuda
+    dt = F16 if feat_prop.dtype == torch.float16 else F32
+    lib = _lib.load()
+    _lib.check(lib.uav_propagate_step(feat_prop.data_ptr(), feat_cur.data_ptr(), flow_prop.data_ptr(),
+                                      flow_check.data_ptr(), out.data_ptr(), Cc, H, W, feat_prop.stride(0),
+                                      feat_cur.stride(0), out.stride(0), flow_prop.stride(0), flow_check.stride(0),
+                                      1 if nearest else 0, 1 if fuse else 0, fuse_scale, alpha1, alpha2,
+                                      1 if half_grid_sample else 0, dt, _stream()), "uav_propagate_step")
+    return out
