@@ -165,6 +165,9 @@ uav_status_t uav_channels_last_to_planar(const void* src, int src_dtype, int64_t
                                          int64_t C, int64_t thw, void* dst, int dst_dtype,
                                          int clamp, uav_stream_t stream);
 uav_status_t uav_silu(const void* x, void* y, int64_t n, uav_stream_t stream);
+/* Fuse_sft_block tail (resnet.py:77-78): out = dec + w * (dec * scale + shift); dense fp16, n % 8 == 0 */
+uav_status_t uav_sft_fuse(const void* dec, const void* scale, const void* shift, float w, void* out,
+                          int64_t n, uav_stream_t stream);
 /* diffusers Timesteps(dim, flip_sin_to_cos, freq_shift) (unet_video.py:173,472): fp32 math, fp16 out */
 uav_status_t uav_timestep_embedding(const float* t, int64_t B, int64_t dim, int flip_sin_to_cos,
                                     float freq_shift, void* out, uav_stream_t stream);

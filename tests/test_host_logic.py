@@ -1,0 +1,83 @@
+"""CPU tests of the host-side logic: C-ABI library loads and exports every declared symbol, header/binding
+agreement, window / chunk planning, and the world_size-2 gloo path of the multi-GPU gather."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol(uav_lib):
+    from upscale_a_video_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "uav_b200.h")).read()
+    declared = set(re.findall(r"\b(uav_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(uav_lib, name), f"{name} declared in include/uav_b200.h but not exported"
+    assert declared == set(_lib.declared_symbols()), (declared ^ set(_lib.declared_symbols()))
+    assert uav_lib.uav_version().decode().startswith("uav_b200")
+    assert uav_lib.uav_launch_count() == 0  # nothing may have launched on a CPU-only box
+
+
+def test_no_cpu_fallback():
+    """the product path must fail loudly without CUDA, never fall back"""
+    from upscale_a_video_b200 import _lib, Propagation
+    with pytest.raises(_lib.UavError):
+        Propagation(4, learnable=False)(torch.zeros(1, 4, 2, 8, 8), torch.zeros(1, 2, 1, 8, 8), torch.zeros(1, 2, 1, 8, 8))
+    src = ""
+    pkg = os.path.join(ROOT, "upscale_a_video_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src += open(os.path.join(pkg, f)).read()
+    assert "import oracle" not in src and "from oracle" not in src, "the product must never import the oracle"
+
+
+def test_window_and_chunk_plans():
+    from oracle import uav_oracle as O
+    from upscale_a_video_b200 import sharding
+    for T in (1, 3, 8, 9, 11, 14, 16, 26, 32, 50, 64):
+        w = sharding.unet_windows(T)
+        if T > 8:
+            assert w == O.unet_windows(T)
+            assert all(e - s == 8 for s, e in w)
+        cover = set()
+        for s, e in w:
+            cover |= set(range(s, e))
+        assert cover == set(range(T))
+        ch = sharding.decode_chunks(T)
+        assert sum(e - s for s, e in ch) == T and ch[0][0] == 0 and ch[-1][1] == T
+    assert sharding.unique(sharding.unet_windows(14)) == [(0, 8), (6, 14)]
+    assert len(sharding.unique(sharding.unet_windows(50))) == 8
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from upscale_a_video_b200 import sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+units = sharding.unique(sharding.unet_windows(26))
+full = [torch.full((2, 4, 8, 3, 5), float(i + 1)) * torch.arange(5) for i in range(len(units))]
+local = {i: full[i] for i in range(len(units)) if i % world == rank}
+out = sharding.all_gather_units(local, len(units), (2, 4, 8, 3, 5), torch.float32, "cpu")
+assert len(out) == len(units)
+for a, b in zip(out, full):
+    assert torch.equal(a, b)
+dist.barrier()
+if rank == 0:
+    print("GATHER_OK")
+"""
+
+
+def test_all_gather_units_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), ROOT],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout + r.stderr

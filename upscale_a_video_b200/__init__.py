@@ -5,3 +5,19 @@ Public surface mirrors the reference (`/root/reference/models_video/`): `VideoUp
 hand-written CUDA kernels behind a C ABI (`include/uav_b200.h`, `csrc/`); there is no CPU path.
 """
 __version__ = "0.1.0"
+
+_LAZY = {
+    "VideoUpscalePipeline": "pipeline_upscale_a_video",
+    "UNetVideoModel": "unet_video",
+    "AutoencoderKLVideo": "autoencoder_kl_cond_video",
+    "DDIMScheduler": "scheduling_ddim",
+    "DDPMScheduler": "scheduling_ddim",
+    "Propagation": "propagation_module",
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
+    raise AttributeError(name)

@@ -49,6 +49,7 @@ _PROTOS = {
     "uav_planar_to_channels_last": [P, I32, I64, I64, I64, P, I64, I64, F32, P],
     "uav_channels_last_to_planar": [P, I32, I64, I64, I64, I64, P, I32, I32, P],
     "uav_silu": [P, P, I64, P],
+    "uav_sft_fuse": [P, P, P, F32, P, I64, P],
     "uav_timestep_embedding": [P, I64, I64, I32, F32, P, P],
     "uav_cfg_combine": [P, P, I64, F32, I32, P],
     "uav_window_blend": [P, I64, P, I64, I64, C.c_uint32, I64, I64, I32, P],

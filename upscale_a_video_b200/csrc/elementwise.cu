@@ -101,6 +101,29 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
   }
 }
 
+
+// Fuse_sft_block tail (resnet.py:77-78): out = dec + w * (dec * scale + shift), 8 halfs per thread
+__global__ void __launch_bounds__(256)
+    sft_fuse_kernel(const __half* __restrict__ dec, const __half* __restrict__ scale,
+                    const __half* __restrict__ shift, float w, __half* __restrict__ out, int64_t n8) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * 256) {
+    const uint4 d = ldg16(dec + i * 8), sc = ldg16(scale + i * 8), sh = ldg16(shift + i * 8);
+    const __half2* dh = reinterpret_cast<const __half2*>(&d);
+    const __half2* ch = reinterpret_cast<const __half2*>(&sc);
+    const __half2* hh = reinterpret_cast<const __half2*>(&sh);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(dh[j]), b = __half22float2(ch[j]), c = __half22float2(hh[j]);
+      __half2 r = __floats2half2_rn(a.x + w * (a.x * b.x + c.x), a.y + w * (a.y * b.y + c.y));
+      ow[j] = *reinterpret_cast<uint32_t*>(&r);
+    }
+    stg16(out + i * 8, o);
+  }
+}
+
 static inline unsigned grid_for(int64_t work, int per_thread = 4) {
   int64_t g = (work + 256 * per_thread - 1) / (256 * per_thread);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
@@ -199,6 +222,17 @@ uav_status_t uav_timestep_embedding(const float* t, int64_t B, int64_t dim, int 
   timestep_embedding_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t, (int)B, (int)dim,
                                                                 flip_sin_to_cos, freq_shift,
                                                                 (__half*)out);
+  UAV_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return UAV_OK;
+}
+
+uav_status_t uav_sft_fuse(const void* dec, const void* scale, const void* shift, float w, void* out,
+                          int64_t n, uav_stream_t stream) {
+  UAV_REQUIRE(dec && scale && shift && out && n >= 0 && n % 8 == 0, "uav_sft_fuse: bad argument");
+  if (n == 0) return UAV_OK;
+  sft_fuse_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)dec, (const __half*)scale, (const __half*)shift, w, (__half*)out, n / 8);
   UAV_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return UAV_OK;

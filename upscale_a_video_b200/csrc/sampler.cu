@@ -22,6 +22,9 @@ struct Num<true> {
   static __device__ __forceinline__ float ld(const __half* p, int64_t i) { return __half2float(p[i]); }
   static __device__ __forceinline__ void st(__half* p, int64_t i, float v) { p[i] = __float2half_rn(v); }
   static __device__ __forceinline__ float rh(float v) { return __half2float(__float2half_rn(v)); }
+  static __device__ __forceinline__ float mul(float a, float b) { return rh(__fmul_rn(a, b)); }
+  static __device__ __forceinline__ float add(float a, float b) { return rh(__fadd_rn(a, b)); }
+  static __device__ __forceinline__ float sub(float a, float b) { return rh(__fsub_rn(a, b)); }
 };
 template <>
 struct Num<false> {
@@ -29,6 +32,10 @@ struct Num<false> {
   static __device__ __forceinline__ float ld(const float* p, int64_t i) { return p[i]; }
   static __device__ __forceinline__ void st(float* p, int64_t i, float v) { p[i] = v; }
   static __device__ __forceinline__ float rh(float v) { return v; }
+  // one torch op == one rounding: intrinsics keep nvcc from contracting a*b+c into an FMA
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 };
 
 #define UAV_GRID_STRIDE(i, n)                                                         \
@@ -43,9 +50,9 @@ __global__ void cfg_kernel(const void* pred2_, void* out_, int64_t n, float g) {
   typename N::T* out = reinterpret_cast<typename N::T*>(out_);
   UAV_GRID_STRIDE(i, n) {
     const float u = N::ld(pred2, i), t = N::ld(pred2, n + i);
-    const float d = N::rh(t - u);
-    const float m = N::rh(g * d);
-    N::st(out, i, u + m);
+    const float d = N::sub(t, u);
+    const float m = N::mul(g, d);
+    N::st(out, i, N::add(u, m));
   }
 }
 
@@ -65,8 +72,8 @@ __global__ void window_blend_kernel(void* dst_, int64_t T, const void* src_, int
     const int64_t di = (o * T + t0 + k) * hw + p;
     const float s = N::ld(src, i);
     if ((covered_mask >> k) & 1u) {
-      const float a = N::rh(N::ld(dst, di) * 0.5f), b = N::rh(s * 0.5f);
-      N::st(dst, di, a + b);
+      const float a = N::mul(N::ld(dst, di), 0.5f), b = N::mul(s, 0.5f);
+      N::st(dst, di, N::add(a, b));
     } else {
       N::st(dst, di, s);
     }
@@ -86,11 +93,11 @@ __global__ void ddim_v0_kernel(const void* mo_, const void* x_, void* x0_, int64
     float r;
     if (pred_type == 0) {
       // (sample - beta^0.5 * eps) / alpha^0.5 ; CUDA divides by a CPU scalar as mul-by-reciprocal
-      r = N::rh(N::rh(s - N::rh(sb * m)) * inv_sa);
+      r = N::mul(N::sub(s, N::mul(sb, m)), inv_sa);
     } else if (pred_type == 1) {
       r = m;
     } else {
-      r = N::rh(N::rh(sa * s) - N::rh(sb * m));
+      r = N::sub(N::mul(sa, s), N::mul(sb, m));
     }
     if (clip) r = fminf(fmaxf(r, -clip_range), clip_range);
     N::st(x0, i, r);
@@ -114,12 +121,12 @@ __global__ void ddim_vt_kernel(const void* x0_, const void* mo_, const void* x_,
     const float m = N::ld(mo, i), s = N::ld(x, i);
     float eps;
     if (pred_type == 0) eps = m;
-    else if (pred_type == 1) eps = N::rh(N::rh(s - N::rh(sa * x0)) * inv_sb);
-    else eps = N::rh(N::rh(sa * m) + N::rh(sb * s));
+    else if (pred_type == 1) eps = N::mul(N::sub(s, N::mul(sa, x0)), inv_sb);
+    else eps = N::add(N::mul(sa, m), N::mul(sb, s));
     if (clip) x0 = fminf(fmaxf(x0, -clip_range), clip_range);
-    const float dir = N::rh(c_dir * eps);
-    float r = N::rh(N::rh(sa_prev * x0) + dir);
-    if (noise != nullptr) r = N::rh(r + N::rh(std * N::ld(noise, i)));
+    const float dir = N::mul(c_dir, eps);
+    float r = N::add(N::mul(sa_prev, x0), dir);
+    if (noise != nullptr) r = N::add(r, N::mul(std, N::ld(noise, i)));
     N::st(prev, i, r);
   }
 }
@@ -133,7 +140,7 @@ __global__ void add_noise_kernel(const void* x_, const void* nz_, void* out_, in
   const typename N::T* nz = reinterpret_cast<const typename N::T*>(nz_);
   typename N::T* out = reinterpret_cast<typename N::T*>(out_);
   UAV_GRID_STRIDE(i, n) {
-    N::st(out, i, N::rh(a * N::ld(x, i)) + N::rh(s * N::ld(nz, i)));
+    N::st(out, i, N::add(N::mul(a, N::ld(x, i)), N::mul(s, N::ld(nz, i))));
   }
 }
 
@@ -152,7 +159,7 @@ struct GridSample {
   using N = Num<HALF>;
   // source index from a normalised coordinate, align_corners=True
   static __device__ __forceinline__ float unnorm(float coord, int size, int half_gs) {
-    const float v = ((coord + 1.f) / 2) * (size - 1);
+    const float v = __fmul_rn(__fadd_rn(coord, 1.f) * 0.5f, static_cast<float>(size - 1));
     return half_gs ? N::rh(v) : v;
   }
   static __device__ __forceinline__ float bilinear(const typename N::T* plane, int H, int W,
@@ -161,16 +168,20 @@ struct GridSample {
     const int ix_ne = ix_nw + 1, iy_ne = iy_nw, ix_sw = ix_nw, iy_sw = iy_nw + 1;
     const int ix_se = ix_nw + 1, iy_se = iy_nw + 1;
     auto r = [&](float v) { return half_gs ? N::rh(v) : v; };
-    const float nw = r(r(ix_se - ix) * r(iy_se - iy));
-    const float ne = r(r(ix - ix_sw) * r(iy_sw - iy));
-    const float sw = r(r(ix_ne - ix) * r(iy - iy_ne));
-    const float se = r(r(ix - ix_nw) * r(iy - iy_nw));
+    const float nw = r(__fmul_rn(r(ix_se - ix), r(iy_se - iy)));
+    const float ne = r(__fmul_rn(r(ix - ix_sw), r(iy_sw - iy)));
+    const float sw = r(__fmul_rn(r(ix_ne - ix), r(iy - iy_ne)));
+    const float se = r(__fmul_rn(r(ix - ix_nw), r(iy - iy_nw)));
     float acc = 0.f;
     auto in = [&](int y, int x) { return y >= 0 && y < H && x >= 0 && x < W; };
-    if (in(iy_nw, ix_nw)) acc = r(acc + r(N::ld(plane, (int64_t)iy_nw * W + ix_nw) * nw));
-    if (in(iy_ne, ix_ne)) acc = r(acc + r(N::ld(plane, (int64_t)iy_ne * W + ix_ne) * ne));
-    if (in(iy_sw, ix_sw)) acc = r(acc + r(N::ld(plane, (int64_t)iy_sw * W + ix_sw) * sw));
-    if (in(iy_se, ix_se)) acc = r(acc + r(N::ld(plane, (int64_t)iy_se * W + ix_se) * se));
+    // `out_acc += inp * w` in ATen's grid_sampler kernel: an FMA per corner in opmath mode
+    auto accum = [&](float v, float w) {
+      acc = half_gs ? N::rh(__fadd_rn(acc, N::rh(__fmul_rn(v, w)))) : __fmaf_rn(v, w, acc);
+    };
+    if (in(iy_nw, ix_nw)) accum(N::ld(plane, (int64_t)iy_nw * W + ix_nw), nw);
+    if (in(iy_ne, ix_ne)) accum(N::ld(plane, (int64_t)iy_ne * W + ix_ne), ne);
+    if (in(iy_sw, ix_sw)) accum(N::ld(plane, (int64_t)iy_sw * W + ix_sw), sw);
+    if (in(iy_se, ix_se)) accum(N::ld(plane, (int64_t)iy_se * W + ix_se), se);
     return N::rh(acc);
   }
   static __device__ __forceinline__ float nearest(const typename N::T* plane, int H, int W,
@@ -201,26 +212,26 @@ __global__ void propagate_step_kernel(const void* feat_prop_, const void* feat_c
     const int y = static_cast<int>(i / W), x = static_cast<int>(i % W);
     const float fpx = N::ld(flow_prop, i), fpy = N::ld(flow_prop, cs_fp + i);
     // flow_warp(): vgrid = grid + flow ; 2.0 * v / max(size-1, 1) - 1.0  (each op rounds)
-    const float gx = N::rh(static_cast<float>(x) + fpx), gy = N::rh(static_cast<float>(y) + fpy);
-    const float vx = N::rh(N::rh(N::rh(2.0f * gx) * inv_wm1) - 1.0f);
-    const float vy = N::rh(N::rh(N::rh(2.0f * gy) * inv_hm1) - 1.0f);
+    const float gx = N::add(static_cast<float>(x), fpx), gy = N::add(static_cast<float>(y), fpy);
+    const float vx = N::sub(N::mul(N::mul(2.0f, gx), inv_wm1), 1.0f);
+    const float vy = N::sub(N::mul(N::mul(2.0f, gy), inv_hm1), 1.0f);
     const float ix = GS::unnorm(vx, W, half_gs), iy = GS::unnorm(vy, H, half_gs);
     // fbConsistencyCheck
     const float bwx = GS::bilinear(flow_check, H, W, ix, iy, half_gs);
     const float bwy = GS::bilinear(flow_check + cs_fc, H, W, ix, iy, half_gs);
-    const float dx = N::rh(fpx + bwx), dy = N::rh(fpy + bwy);
-    const float lsq_f = N::rh(N::rh(fpx * fpx) + N::rh(fpy * fpy));
-    const float lsq_b = N::rh(N::rh(bwx * bwx) + N::rh(bwy * bwy));
-    const float mag = N::rh(lsq_f + lsq_b);
-    const float thr = N::rh(N::rh(alpha1 * mag) + alpha2);
-    const float lsq_d = N::rh(N::rh(dx * dx) + N::rh(dy * dy));
+    const float dx = N::add(fpx, bwx), dy = N::add(fpy, bwy);
+    const float lsq_f = N::add(N::mul(fpx, fpx), N::mul(fpy, fpy));
+    const float lsq_b = N::add(N::mul(bwx, bwx), N::mul(bwy, bwy));
+    const float mag = N::add(lsq_f, lsq_b);
+    const float thr = N::add(N::mul(alpha1, mag), alpha2);
+    const float lsq_d = N::add(N::mul(dx, dx), N::mul(dy, dy));
     const float mask = (lsq_d < thr) ? 1.f : 0.f;
     for (int c = 0; c < C; ++c) {
       const T* plane = feat_prop + c * cs_prop;
       float w = nearest ? GS::nearest(plane, H, W, ix, iy) : GS::bilinear(plane, H, W, ix, iy, half_gs);
       const float cur = N::ld(feat_cur, c * cs_cur + i);
-      if (fuse) w = N::rh(N::rh(w * fuse_scale) + N::rh(cur * (1.f - fuse_scale)));
-      const float r = N::rh(N::rh(mask * w) + N::rh(N::rh(1.f - mask) * cur));
+      if (fuse) w = N::add(N::mul(w, fuse_scale), N::mul(cur, 1.f - fuse_scale));
+      const float r = N::add(N::mul(mask, w), N::mul(N::sub(1.f, mask), cur));
       N::st(out, c * cs_out + i, r);
     }
   }

@@ -148,12 +148,31 @@ class InflatedConv3d(nn.Conv2d):
                 xp = torch.zeros(*x.shape[:-3], H + H % 2, W + W % 2, x.shape[-1], dtype=x.dtype, device=x.device)
                 xp[..., :H, :W, :].copy_(x)  # strided plumbing copy (only for odd sizes, e.g. 45 -> 23 at 180x320)
                 x = xp
-            return ops.conv2d(x, w, b, stride=2, pad_mode=pad_mode, **epi)
-        return ops.conv2d(x, w, b, **epi)
+            return self._launch(x, w, b, dict(stride=2, pad_mode=pad_mode), epi)
+        return self._launch(x, w, b, {}, epi)
+
+    @staticmethod
+    def _launch(x, w, b, kw, epi):
+        cout = w.shape[0]
+        if cout % 8 and epi.get("out") is None and epi.get("out_dtype", torch.float16) == torch.float16:
+            # keep the channels-last invariant "pixel stride % 8 == 0": zero-padded buffer, conv writes [:cout];
+            # downstream filters are zero-padded on Cin, so the pad channels contribute exactly 0
+            H, W = x.shape[-3], x.shape[-2]
+            if kw.get("stride", 1) == 2:
+                H, W = H // 2, W // 2
+            buf = torch.zeros(*x.shape[:-3], H, W, _pad8(cout), dtype=torch.float16, device=x.device)
+            ops.conv2d(x, w, b, out=buf[..., :cout], **kw, **epi)
+            return buf
+        return ops.conv2d(x, w, b, **kw, **epi)
 
 
 def _gn(c: Ctx, norm: nn.GroupNorm, x, silu: bool, n_outer: int):
     g, b = c.pk.affine(norm)
+    C = norm.num_channels
+    if x.shape[-1] != C:  # logical C channels inside a zero-padded buffer (e.g. the 3-channel LR frames)
+        out = torch.zeros_like(x)
+        ops.group_norm(x[..., :C], g, b, norm.num_groups, norm.eps, silu=silu, n_outer=n_outer, out=out[..., :C])
+        return out
     return ops.group_norm(x, g, b, norm.num_groups, norm.eps, silu=silu, n_outer=n_outer)
 
 
@@ -581,3 +600,117 @@ class CrossAttnUpBlock3D(UpBlock3D):
                          resnet_groups, add_upsample)
         self.attentions = nn.ModuleList([_t3d(attn_num_head_channels, out_channels, cross_attention_dim, resnet_groups,
                                               only_cross_attention, rotary_emb) for _ in range(num_layers)])
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE side of unet_blocks.py / vae_video.py
+# ------------------------------------------------------------------------------------------------
+class AttentionBlock(nn.Module):
+    """diffusers AttentionBlock (unet_blocks.py:16,703-713; in-tree copy diffusers_attention.py:249-381):
+    per-frame single-head attention over all h*w positions, d = channels."""
+
+    def __init__(self, channels, num_head_channels=None, norm_num_groups=32, rescale_output_factor=1.0, eps=1e-5):
+        super().__init__()
+        self.channels = channels
+        self.num_heads = channels // num_head_channels if num_head_channels is not None else 1
+        assert rescale_output_factor == 1.0
+        self.group_norm = nn.GroupNorm(num_channels=channels, num_groups=norm_num_groups, eps=eps, affine=True)
+        self.query = nn.Linear(channels, channels)
+        self.key = nn.Linear(channels, channels)
+        self.value = nn.Linear(channels, channels)
+        self.proj_attn = nn.Linear(channels, channels, bias=True)
+        self._use_memory_efficient_attention_xformers = False  # read by the pipeline (pipeline...:673)
+
+    def forward(self, c: Ctx, x):
+        B, T, H, W, C = x.shape
+        n = _gn(c, self.group_norm, x, False, B * T)
+        w, b = c.pk.fused_linear(f"qkv{id(self)}", [self.query, self.key, self.value])
+        qkv = ops.linear(n.view(B * T, H * W, C), w, b)
+        o = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_heads,
+                          scale=(C // self.num_heads) ** -0.5)
+        wo, bo = c.pk.linear(self.proj_attn)
+        return ops.linear(o, wo, bo, residual=x.view(B * T, H * W, C)).view(B, T, H, W, C)
+
+
+def _vae_resnet(plus: bool, cin, cout, eps, groups):
+    cls = ResnetBlock3D_plus if plus else ResnetBlock3D
+    return cls(in_channels=cin, out_channels=cout, temb_channels=None, eps=eps, groups=groups)
+
+
+class UNetMidBlock3D(nn.Module):
+    """unet_blocks.py:663-745 (and the `_plus` variant :848-915)"""
+    PLUS = False
+
+    def __init__(self, in_channels, resnet_eps=1e-6, resnet_groups=32, attn_num_head_channels=None, **_):
+        super().__init__()
+        self.resnets = nn.ModuleList([_vae_resnet(self.PLUS, in_channels, in_channels, resnet_eps, resnet_groups)
+                                      for _ in range(2)])
+        self.attentions = nn.ModuleList([AttentionBlock(in_channels, num_head_channels=attn_num_head_channels,
+                                                        eps=resnet_eps, norm_num_groups=resnet_groups)])
+
+    def forward(self, c: Ctx, x):
+        x = self.resnets[0](c, x)
+        x = self.attentions[0](c, x)
+        return self.resnets[1](c, x)
+
+
+class UNetMidBlock3D_plus(UNetMidBlock3D):
+    PLUS = True
+
+
+class DownEncoderBlock3D(nn.Module):
+    """unet_blocks.py:748-805"""
+
+    def __init__(self, in_channels, out_channels, num_layers=1, resnet_eps=1e-6, resnet_groups=32, add_downsample=True,
+                 downsample_padding=1, **_):
+        super().__init__()
+        self.resnets = nn.ModuleList([_vae_resnet(False, in_channels if i == 0 else out_channels, out_channels,
+                                                  resnet_eps, resnet_groups) for i in range(num_layers)])
+        self.downsamplers = (nn.ModuleList([Downsample3D(out_channels, True, out_channels, downsample_padding, "op")])
+                             if add_downsample else None)
+
+    def forward(self, c: Ctx, x):
+        for r in self.resnets:
+            x = r(c, x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](c, x)
+        return x
+
+
+class UpDecoderBlock3D(nn.Module):
+    """unet_blocks.py:808-845 (and `_plus` :918-993)"""
+    PLUS = False
+
+    def __init__(self, in_channels, out_channels, num_layers=1, resnet_eps=1e-6, resnet_groups=32, add_upsample=True, **_):
+        super().__init__()
+        self.resnets = nn.ModuleList([_vae_resnet(self.PLUS, in_channels if i == 0 else out_channels, out_channels,
+                                                  resnet_eps, resnet_groups) for i in range(num_layers)])
+        self.upsamplers = nn.ModuleList([Upsample3D(out_channels, True, out_channels)]) if add_upsample else None
+
+    def forward(self, c: Ctx, x):
+        for r in self.resnets:
+            x = r(c, x)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](c, x)
+        return x
+
+
+class UpDecoderBlock3D_plus(UpDecoderBlock3D):
+    PLUS = True
+
+
+class Fuse_sft_block(nn.Module):
+    """resnet.py:63-79"""
+
+    def __init__(self, enc_ch, dec_ch):
+        super().__init__()
+        self.shared = nn.Sequential(ResnetBlock3D(in_channels=enc_ch + dec_ch, out_channels=dec_ch, temb_channels=None),
+                                    ResnetBlock3D(in_channels=dec_ch, out_channels=dec_ch, temb_channels=None))
+        self.scale = InflatedConv3d(dec_ch, dec_ch, 3, 1, 1)
+        self.shift = InflatedConv3d(dec_ch, dec_ch, 3, 1, 1)
+
+    def forward(self, c: Ctx, enc_feat, dec_feat, w=1):
+        e = ops.concat_channels(enc_feat, dec_feat)
+        e = self.shared[0](c, e)
+        e = self.shared[1](c, e)
+        return ops.sft_fuse(dec_feat, self.scale.run(c, e), self.shift.run(c, e), float(w))

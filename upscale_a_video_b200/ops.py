@@ -281,6 +281,17 @@ def silu(x: torch.Tensor):
     return out
 
 
+def sft_fuse(dec: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, w: float):
+    """dec + w * (dec * scale + shift) (Fuse_sft_block, resnet.py:77-78); dense fp16 tensors of equal shape"""
+    for t in (dec, scale, shift):
+        assert t.dtype == torch.float16 and t.is_contiguous() and t.shape == dec.shape
+    out = torch.empty_like(dec)
+    lib = _lib.load()
+    _lib.check(lib.uav_sft_fuse(dec.data_ptr(), scale.data_ptr(), shift.data_ptr(), float(w), out.data_ptr(), dec.numel(),
+                                _stream()), "uav_sft_fuse")
+    return out
+
+
 def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float):
     assert t.dtype == torch.float32 and t.is_contiguous()
     out = torch.empty(t.shape[0], dim, dtype=torch.float16, device=t.device)
