@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — upscaled frames/sec of the Upscale-A-Video sampling path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # uav_b200 arm (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference [--gpus N] ...              # reference arm: the path's own CPU implementation
+
+One "step" = one full pass of the hot path over one synthetic clip: `VideoUpscalePipeline.__call__` with 30 DDIM
+steps (chunked UNet, CFG, step_v0, flow propagation at steps 24/26/28, step_vt) followed by the chunked VAE decode.
+N=1 runs BASELINE.json configs[1]: 8 frames 320x576 -> 1280x2304, guidance 6, fp16.  N>1 is weak scaling: the clip
+has 8 + 6*(N-1) frames, i.e. exactly N unique 8-frame UNet windows per DDIM step (one per rank) and ceil(T/3) decode
+chunks dealt over ranks; one NCCL all_gather per DDIM step + one at the end (upscale_a_video_b200/sharding.py).
+
+`value`: frames/s with inputs resident in HBM, CUDA-event timed, max over ranks.  `e2e`: same through the public API
+with pinned HOST buffers (H2D of the LR clip + flows, D2H of the decoded frames inside the timed region).
+Weights are random-init (no checkpoints offline), inputs synthetic (seeded) — see `data`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# algorithmic work
+UNET_TFLOP_PER_FWD_C2 = 319.96     # B=2, T=8, 320x576
+VAE_TFLOP_PER_3F_C2 = 294.6        # 3-frame chunk, 320x576, vae_3d
+H_LR, W_LR, STEPS_DDIM, GUIDANCE, NOISE_LEVEL = 320, 576, 30, 6.0, 120
+PROP_STEPS = [24, 26, 28]
+
+
+def frames_for(n_gpus):
+    return 8 + 6 * (n_gpus - 1)
+
+
+def synth_inputs(T, H, W, device):
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand(1, 3, T, H, W, generator=g) * 2 - 1
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    fw = torch.stack([3.0 * torch.sin(yy / 7.0 + 0.3) + 0 * xx, 3.0 * torch.cos(xx / 5.0) + 0 * yy])
+    g1 = torch.Generator().manual_seed(1)
+    fw = fw[None, :, None].repeat(1, 1, T - 1, 1, 1) + 0.5 * torch.randn(1, 2, T - 1, H, W, generator=g1)
+    bw = -fw + 0.4 * torch.randn(1, 2, T - 1, H, W, generator=g1)
+    g2 = torch.Generator().manual_seed(2)
+    pe = torch.randn(2, 77, 1024, generator=g2) * 0.3
+    return image, fw, bw, pe
+
+
+def seeded_state_dict(module, seed):
+    from oracle.weights import make_state_dict  # deterministic random init (no checkpoints exist offline)
+    return make_state_dict({k: tuple(v.shape) for k, v in module.state_dict().items()}, seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_pipeline(device):
+    from upscale_a_video_b200 import (AutoencoderKLVideo, DDIMScheduler, DDPMScheduler, Propagation, UNetVideoModel,
+                                      VideoUpscalePipeline)
+    cfgdir = os.path.join(ROOT, "upscale_a_video_b200", "configs")
+    unet = UNetVideoModel.from_config(json.load(open(os.path.join(cfgdir, "unet_video_config.json"))))
+    unet.load_state_dict(seeded_state_dict(unet, 1234), strict=True)
+    unet = unet.half().eval().to(device)
+    vae = AutoencoderKLVideo.from_config(json.load(open(os.path.join(cfgdir, "vae_3d_config.json"))))
+    vae.load_state_dict(seeded_state_dict(vae, 4321), strict=True)
+    vae = vae.eval().to(device)
+    sched = DDIMScheduler(beta_schedule="scaled_linear", clip_sample=False, steps_offset=1, prediction_type="v_prediction",
+                          set_alpha_to_one=False)  # SD-x4-upscaler style
+    return VideoUpscalePipeline(text_encoder=None, tokenizer=None, low_res_scheduler=DDPMScheduler(beta_schedule="scaled_linear"),
+                                scheduler=sched, vae=vae, unet=unet, propagator=Propagation(4, learnable=False))
+
+
+def cpu_baseline_sample(threads=None):
+    """the oracle (CPU port of the reference path) on a bounded sample, scaled by algorithmic FLOPs"""
+    from oracle import uav_oracle as O
+    from oracle.weights import make_state_dict
+    torch.set_num_threads(threads or os.cpu_count())
+    cfgdir = os.path.join(ROOT, "upscale_a_video_b200", "configs")
+    ucfg = json.load(open(os.path.join(cfgdir, "unet_video_config.json")))
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "shapes_unet.json")))
+    sd = make_state_dict(shapes, 1234)
+    B, T, H, W = 2, 2, 64, 96
+    g = torch.Generator().manual_seed(0)
+    sample, low = torch.randn(B, 4, T, H, W, generator=g), torch.randn(B, 3, T, H, W, generator=g)
+    ctx = torch.randn(B, 77, 1024, generator=g) * 0.3
+    with torch.no_grad():
+        O.unet_forward(sd, ucfg, sample[:, :, :1, :32, :32], torch.tensor(500), low[:, :, :1, :32, :32], ctx, torch.tensor([120]))
+        t0 = time.time()
+        O.unet_forward(sd, ucfg, sample, torch.tensor(500), low, ctx, torch.tensor([120]))
+        dt = time.time() - t0
+    # UNet work scales ~linearly in T*H*W away from the self-attention term
+    tflop = UNET_TFLOP_PER_FWD_C2 * (T * H * W) / (8 * H_LR * W_LR)
+    cpu_tflops = tflop / dt
+    per_frame_tflop = STEPS_DDIM * UNET_TFLOP_PER_FWD_C2 / 8 + VAE_TFLOP_PER_3F_C2 / 3
+    return {"value": cpu_tflops / per_frame_tflop, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle UNet forward B=2,T={T},{H}x{W} fp32 ({tflop:.2f} TFLOP algorithmic) in {dt:.1f} s = "
+                      f"{cpu_tflops:.3f} TFLOP/s, scaled by algorithmic FLOPs/frame ({per_frame_tflop:.0f} TFLOP) to config 2"}
+
+
+def run_reference_arm(args):
+    """the reference's own CPU implementation of the path (oracle port; /root/reference does not exist on the GPU box)"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline_sample()
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    T = frames_for(args.gpus)
+    print(json.dumps({"impl": "reference", "metric": "upscaled frames/sec (30 DDIM steps, 320x576->4x)", "value": v,
+                      "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1000.0 * T / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic, random-init weights",
+                      "config": {"workload": f"{T}-frame 320x576->1280x2304, 30 DDIM steps, guidance 6 (CPU: bounded sample, FLOP-scaled)"},
+                      "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="uav_b200")
+    ap.add_argument("--ddim-steps", type=int, default=STEPS_DDIM, help=argparse.SUPPRESS)  # debugging only
+    ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from upscale_a_video_b200 import _lib, build, ops
+    build.build()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    T = frames_for(args.gpus)
+    pipe = build_pipeline(device)
+    image, fw, bw, pe = synth_inputs(T, H_LR, W_LR, device)
+    neg, pos = pe.half().to(device).chunk(2)
+    kw = dict(num_inference_steps=args.ddim_steps, guidance_scale=GUIDANCE, noise_level=NOISE_LEVEL,
+              propagation_steps=[s for s in PROP_STEPS if s < args.ddim_steps], prompt_embeds=pos, negative_prompt_embeds=neg)
+    d_image, d_fw, d_bw = image.to(device), fw.to(device), bw.to(device)
+    h_image, h_fw, h_bw = image.pin_memory(), fw.pin_memory(), bw.pin_memory()
+    h_out = torch.empty(1, 3, T, 4 * H_LR, 4 * W_LR, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        gen = torch.Generator(device=device).manual_seed(10)  # inference_upscale_a_video.py:197
+        return pipe(None, image=d_image, flows_bi=[d_fw, d_bw], generator=gen, **kw).images
+
+    def step_e2e():
+        gen = torch.Generator(device=device).manual_seed(10)
+        img = h_image.to(device, non_blocking=True)
+        flows = [h_fw.to(device, non_blocking=True), h_bw.to(device, non_blocking=True)]
+        out = pipe(None, image=img, flows_bi=flows, generator=gen, **kw).images
+        h_out.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - l0
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # roofline of the dominant kernel (tcgen05 implicit GEMM): per-launch CUDA events over one UNet forward
+    roof = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        lat = torch.randn(2, 4, 8, H_LR, W_LR, device=device, dtype=torch.float16)
+        low = torch.randn(2, 3, 8, H_LR, W_LR, device=device, dtype=torch.float16)
+        ctx = torch.cat([neg, pos])
+        pipe.unet(lat, 500, low, encoder_hidden_states=ctx, class_labels=torch.tensor([NOISE_LEVEL]))
+        with ops.Profile() as prof:
+            pipe.unet(lat, 500, low, encoder_hidden_states=ctx, class_labels=torch.tensor([NOISE_LEVEL]))
+        summ = prof.summary()
+        ig = summ.get("igemm", dict(flops=0.0, ms=1.0, launches=1))
+        tot_ms = sum(d["ms"] for d in summ.values())
+        achieved = ig["flops"] / ig["ms"] / 1e9
+        roof = {"bound": "tensor", "kernel": "uav::igemm_kernel (tcgen05 implicit GEMM: conv2d/conv_t/linear)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": which, "launches_per_unet_forward": ig["launches"],
+                "share_of_unet_forward_time": ig["ms"] / tot_ms,
+                "per_kind_ms": {k: round(d["ms"], 3) for k, d in summ.items()},
+                "hbm_bound_kinds_GBps": {k: round(d["bytes"] / d["ms"] / 1e6, 1) for k, d in summ.items() if d["flops"] == 0.0}}
+
+    if rank == 0:
+        fps = T * args.steps / (ms_total / 1000.0)
+        fps_e2e = T * args.steps / (ms_e2e / 1000.0)
+        cb = None if args.no_cpu_baseline or args.gpus != 1 else cpu_baseline_sample()
+        line = {"metric": "upscaled frames/sec (30 DDIM steps, 320x576->4x)", "value": fps, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic (seeded LR clip, smooth flows, random prompt embeddings), random-init weights of the shipped configs",
+                "config": {"workload": f"{T}-frame 320x576->1280x2304, {args.ddim_steps} DDIM steps, guidance 6, propagation at {kw['propagation_steps']}, vae_3d decode",
+                           "frames": T, "unet_windows_per_step": T // 6 if T > 8 else 1, "parallelism": f"windows/chunks over {args.gpus} GPU(s)",
+                           "l2": "inputs larger than L2 (activations 0.4-4.5 GB per layer)"},
+                "e2e": {"value": fps_e2e, "unit": "frames/s",
+                        "h2d_bytes_per_step": int(h_image.numel() * 4 + h_fw.numel() * 4 + h_bw.numel() * 4),
+                        "d2h_bytes_per_step": int(h_out.numel() * 4)},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

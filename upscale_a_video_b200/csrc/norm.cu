@@ -14,67 +14,60 @@ namespace uav {
 extern std::atomic<uint64_t> g_launches;
 
 constexpr int GN_THREADS = 256;
-constexpr int GN_MAX_UNITS = 512;  // 4-channel units: C <= 2048
 
 // ---------------------------------------------------------------------------------------
-// stats: sums[n][g] = {sum, sumsq} (fp64) over the group's channels and all pixels
+// stats, deterministic (no atomics): every block writes its {sum, sumsq} per group to
+// partial[n][block][g]; gn_finalize_kernel reduces the blocks in a fixed order in fp64.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_THREADS)
     gn_stats_kernel(const __half* __restrict__ x, int64_t pixels, int C, int64_t ld, int G,
-                    double* __restrict__ sums) {
-  __shared__ float s_sum[GN_MAX_UNITS];
-  __shared__ float s_sq[GN_MAX_UNITS];
+                    float2* __restrict__ partial) {
+  // [pixel lane][unit] partial sums; pixel lanes * units == 2 * GN_THREADS
+  __shared__ float s_sum[2 * GN_THREADS];
+  __shared__ float s_sq[2 * GN_THREADS];
   const int n = blockIdx.y;
-  const int octs = C >> 3;  // 8-channel vectors per pixel
-  const int units = C >> 2;
-  for (int i = threadIdx.x; i < units; i += GN_THREADS) {
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
-  }
-  __syncthreads();
+  const int octs = C >> 3;   // 8-channel vectors per pixel (<= 256)
+  const int units = C >> 2;  // 4-channel units
   const __half* xn = x + static_cast<int64_t>(n) * pixels * ld;
-  // thread -> (pixel lane, octet); octs may exceed the block (C = 2048 -> 256 octets)
-  const int oct_per_pass = octs < GN_THREADS ? octs : GN_THREADS;
-  const int pix_per_iter = GN_THREADS / oct_per_pass;
-  const int my_pix = threadIdx.x / oct_per_pass;
-  const int my_oct0 = threadIdx.x % oct_per_pass;
+  const int pix_per_iter = GN_THREADS / octs;
+  const int my_pix = threadIdx.x / octs;
+  const int oct = threadIdx.x % octs;
+  float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
   if (my_pix < pix_per_iter) {
-    for (int oct = my_oct0; oct < octs; oct += oct_per_pass) {
-      float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
-      for (int64_t p = static_cast<int64_t>(blockIdx.x) * pix_per_iter + my_pix; p < pixels;
-           p += static_cast<int64_t>(gridDim.x) * pix_per_iter) {
-        const uint4 v = ldg16(xn + p * ld + oct * 8);
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-        const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-        a0 += f0.x + f0.y + f1.x + f1.y;
-        q0 += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;
-        a1 += f2.x + f2.y + f3.x + f3.y;
-        q1 += f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
-      }
-      atomicAdd(&s_sum[oct * 2], a0);
-      atomicAdd(&s_sq[oct * 2], q0);
-      atomicAdd(&s_sum[oct * 2 + 1], a1);
-      atomicAdd(&s_sq[oct * 2 + 1], q1);
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * pix_per_iter + my_pix; p < pixels;
+         p += static_cast<int64_t>(gridDim.x) * pix_per_iter) {
+      const uint4 v = ldg16(xn + p * ld + oct * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+      const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+      a0 += f0.x + f0.y + f1.x + f1.y;
+      q0 += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;
+      a1 += f2.x + f2.y + f3.x + f3.y;
+      q1 += f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
     }
+    s_sum[my_pix * units + oct * 2] = a0;
+    s_sq[my_pix * units + oct * 2] = q0;
+    s_sum[my_pix * units + oct * 2 + 1] = a1;
+    s_sq[my_pix * units + oct * 2 + 1] = q1;
   }
   __syncthreads();
   const int units_per_group = units / G;  // (C/G)/4
   for (int g = threadIdx.x; g < G; g += GN_THREADS) {
-    double s = 0.0, q = 0.0;
-    for (int u = 0; u < units_per_group; ++u) {
-      s += s_sum[g * units_per_group + u];
-      q += s_sq[g * units_per_group + u];
-    }
-    atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2], s);
-    atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2 + 1], q);
+    float s = 0.f, q = 0.f;
+    for (int pl = 0; pl < pix_per_iter; ++pl)
+      for (int u = 0; u < units_per_group; ++u) {
+        s += s_sum[pl * units + g * units_per_group + u];
+        q += s_sq[pl * units + g * units_per_group + u];
+      }
+    partial[(static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * G + g] = make_float2(s, q);
   }
 }
 
 // generic scalar statistics (any C, any G): used for tiny channel counts (C = 3)
 __global__ void __launch_bounds__(GN_THREADS)
     gn_stats_generic_kernel(const __half* __restrict__ x, int64_t pixels, int C, int64_t ld, int G,
-                            double* __restrict__ sums) {
+                            float2* __restrict__ partial) {
+  __shared__ float s_s[GN_THREADS / 32], s_q[GN_THREADS / 32];
   const int n = blockIdx.y;
   const int cpg = C / G;
   const __half* xn = x + static_cast<int64_t>(n) * pixels * ld;
@@ -93,9 +86,35 @@ __global__ void __launch_bounds__(GN_THREADS)
       q += __shfl_xor_sync(0xffffffff, q, o);
     }
     if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2], static_cast<double>(s));
-      atomicAdd(&sums[(static_cast<int64_t>(n) * G + g) * 2 + 1], static_cast<double>(q));
+      s_s[threadIdx.x >> 5] = s;
+      s_q[threadIdx.x >> 5] = q;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float ts = 0.f, tq = 0.f;
+      for (int w = 0; w < GN_THREADS / 32; ++w) {
+        ts += s_s[w];
+        tq += s_q[w];
+      }
+      partial[(static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * G + g] = make_float2(ts, tq);
+    }
+    __syncthreads();
+  }
+}
+
+// sums[n][g] = fixed-order fp64 reduction of the per-block partials
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int nblocks, int G,
+                                   double* __restrict__ sums) {
+  const int n = blockIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      const float2 v = partial[(static_cast<int64_t>(n) * nblocks + b) * G + g];
+      s += v.x;
+      q += v.y;
+    }
+    sums[(static_cast<int64_t>(n) * G + g) * 2] = s;
+    sums[(static_cast<int64_t>(n) * G + g) * 2 + 1] = q;
   }
 }
 
@@ -242,8 +261,11 @@ using namespace uav;
 
 extern "C" {
 
+static constexpr int GN_MAX_BLOCKS_PER_N = 2048;  // upper bound of gridDim.x of the stats kernels
+
 size_t uav_groupnorm_workspace_bytes(int64_t n_outer, int groups) {
-  return static_cast<size_t>(n_outer) * groups * 2 * sizeof(double);
+  // fp64 {sum, sumsq} per (n, group)  +  fp32 {sum, sumsq} per (n, block, group)
+  return static_cast<size_t>(n_outer) * groups * (2 * sizeof(double) + GN_MAX_BLOCKS_PER_N * sizeof(float2));
 }
 
 uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, int64_t C,
@@ -259,33 +281,35 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
   UAV_REQUIRE(n_outer <= 65535, "uav_groupnorm_silu: n_outer too large");
   UAV_REQUIRE(workspace_bytes >= uav_groupnorm_workspace_bytes(n_outer, groups),
               "uav_groupnorm_silu: workspace too small");
-  UAV_CHECK_CUDA(
-      cudaMemsetAsync(workspace, 0, uav_groupnorm_workspace_bytes(n_outer, groups), stream));
   double* sums = reinterpret_cast<double*>(workspace);
+  float2* partial = reinterpret_cast<float2*>(sums + n_outer * groups * 2);
   const int cpg = (int)(C / groups);
   const bool vec = (C % 8 == 0) && (cpg % 4 == 0) && (ld_in % 8 == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const int sms = num_sms();
+  int64_t gx;
   if (vec) {
     const int octs = (int)(C / 8);
-    const int oct_per_pass = octs < GN_THREADS ? octs : GN_THREADS;
-    const int pix_per_iter = GN_THREADS / oct_per_pass;
+    const int pix_per_iter = GN_THREADS / octs;
     int64_t want = (sms * 8 + n_outer - 1) / n_outer;
     int64_t maxb = (pixels + pix_per_iter - 1) / pix_per_iter;
-    // at least ~16 pixels per thread-iteration chain to amortise the smem atomics
-    maxb = (maxb + 15) / 16;
-    int64_t gx = want < maxb ? want : maxb;
+    maxb = (maxb + 15) / 16;  // >= ~16 pixels per thread to amortise the block reduction
+    gx = want < maxb ? want : maxb;
     if (gx < 1) gx = 1;
+    if (gx > GN_MAX_BLOCKS_PER_N) gx = GN_MAX_BLOCKS_PER_N;
     gn_stats_kernel<<<dim3((unsigned)gx, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
-        reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums);
+        reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, partial);
   } else {
     int64_t want = (sms * 4 + n_outer - 1) / n_outer;
     int64_t maxb = (pixels + GN_THREADS - 1) / GN_THREADS;
-    int64_t gx = want < maxb ? want : maxb;
+    gx = want < maxb ? want : maxb;
     if (gx < 1) gx = 1;
+    if (gx > GN_MAX_BLOCKS_PER_N) gx = GN_MAX_BLOCKS_PER_N;
     gn_stats_generic_kernel<<<dim3((unsigned)gx, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
-        reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums);
+        reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, partial);
   }
+  UAV_CHECK_CUDA(cudaGetLastError());
+  gn_finalize_kernel<<<(unsigned)n_outer, 64, 0, stream>>>(partial, (int)gx, groups, sums);
   UAV_CHECK_CUDA(cudaGetLastError());
   {
     const bool vec_apply = (C % 8 == 0) && (ld_in % 8 == 0) && (ld_out % 8 == 0) &&
@@ -304,7 +328,7 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
                                 ld_out);
   }
   UAV_CHECK_CUDA(cudaGetLastError());
-  g_launches.fetch_add(2, std::memory_order_relaxed);
+  g_launches.fetch_add(3, std::memory_order_relaxed);
   return UAV_OK;
 }
 

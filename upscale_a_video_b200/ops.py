@@ -22,6 +22,52 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class Profile:
+    """Opt-in per-launch timing (CUDA events on the launching stream) + algorithmic work counters, used by bench.py
+    for the roofline numbers.  Disabled (zero overhead) unless entered as a context manager."""
+    active: "Optional[Profile]" = None
+
+    def __init__(self):
+        self.records = []  # (kind, flops, bytes, start_event, end_event)
+
+    def __enter__(self):
+        Profile.active = self
+        return self
+
+    def __exit__(self, *a):
+        Profile.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, fl, by, s, e in self.records:
+            d = out.setdefault(kind, dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+            d["ms"] += s.elapsed_time(e)
+        return out
+
+
+class _timed:
+    __slots__ = ("kind", "flops", "bytes", "s")
+
+    def __init__(self, kind, flops=0.0, nbytes=0.0):
+        self.kind, self.flops, self.bytes = kind, flops, nbytes
+
+    def __enter__(self):
+        if Profile.active is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *a):
+        p = Profile.active
+        if p is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            p.records.append((self.kind, self.flops, self.bytes, self.s, e))
+
+
 def _pixel_ld(x: torch.Tensor) -> int:
     """element distance between consecutive pixels; validates the channels-last layout"""
     assert x.is_cuda, "uav_b200 ops need CUDA tensors (no CPU fallback)"
@@ -72,8 +118,9 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     assert out.shape[-1] == n_out and out.numel() // n_out == M
     e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
     lib = _lib.load()
-    _lib.check(lib.uav_linear(a.data_ptr(), M, K, _pixel_ld(a) if a.dim() > 1 else K, w.data_ptr(), N,
-                              out.data_ptr(), C.byref(e), _stream()), "uav_linear")
+    with _timed("igemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out)):
+        _lib.check(lib.uav_linear(a.data_ptr(), M, K, _pixel_ld(a) if a.dim() > 1 else K, w.data_ptr(), N,
+                                  out.data_ptr(), C.byref(e), _stream()), "uav_linear")
     return out
 
 
@@ -93,8 +140,10 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, pad_mode=0,
     assert tuple(out.shape) == (*lead, Ho, Wo, Cout), (out.shape, (*lead, Ho, Wo, Cout))
     e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
     lib = _lib.load()
-    _lib.check(lib.uav_conv2d(x.data_ptr(), NB, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k, stride,
-                              pad_mode, out.data_ptr(), C.byref(e), _stream()), "uav_conv2d")
+    with _timed("igemm", 2.0 * NB * Ho * Wo * Cout * Cin * k * k,
+                2.0 * (NB * H * W * Cin + w.numel()) + out.element_size() * NB * Ho * Wo * Cout):
+        _lib.check(lib.uav_conv2d(x.data_ptr(), NB, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k, stride,
+                                  pad_mode, out.data_ptr(), C.byref(e), _stream()), "uav_conv2d")
     return out
 
 
@@ -109,8 +158,9 @@ def conv_temporal(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, resi
         out = torch.empty(B, T, H, W, Cout, dtype=out_dtype, device=x.device)
     e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
     lib = _lib.load()
-    _lib.check(lib.uav_conv_temporal(x.data_ptr(), B, T, H * W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k,
-                                     out.data_ptr(), C.byref(e), _stream()), "uav_conv_temporal")
+    with _timed("igemm", 2.0 * B * T * H * W * Cout * Cin * k, 2.0 * (x.numel() + w.numel() + B * T * H * W * Cout)):
+        _lib.check(lib.uav_conv_temporal(x.data_ptr(), B, T, H * W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k,
+                                         out.data_ptr(), C.byref(e), _stream()), "uav_conv_temporal")
     return out
 
 
@@ -125,8 +175,9 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=No
         out = torch.empty(B, T, H, W, Cout, dtype=out_dtype, device=x.device)
     e = _epi(out, bias, None, 0, residual, act)
     lib = _lib.load()
-    _lib.check(lib.uav_conv3d(x.data_ptr(), B, T, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout,
-                              out.data_ptr(), C.byref(e), _stream()), "uav_conv3d")
+    with _timed("igemm", 2.0 * B * T * H * W * Cout * Cin * 27, 2.0 * (x.numel() + w.numel() + B * T * H * W * Cout)):
+        _lib.check(lib.uav_conv3d(x.data_ptr(), B, T, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout,
+                                  out.data_ptr(), C.byref(e), _stream()), "uav_conv3d")
     return out
 
 
@@ -159,9 +210,10 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     lib = _lib.load()
     nbytes = lib.uav_groupnorm_workspace_bytes(n_outer, groups)
     ws = _gn_workspace(x.device, nbytes)
-    _lib.check(lib.uav_groupnorm_silu(x.data_ptr(), n_outer, pixels, C, _pixel_ld(x), groups, gamma.data_ptr(),
-                                      beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), _pixel_ld(out),
-                                      ws.data_ptr(), ws.numel(), _stream()), "uav_groupnorm_silu")
+    with _timed("groupnorm", 0.0, 2.0 * 3 * total_pix * C):  # read (stats) + read + write
+        _lib.check(lib.uav_groupnorm_silu(x.data_ptr(), n_outer, pixels, C, _pixel_ld(x), groups, gamma.data_ptr(),
+                                          beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), _pixel_ld(out),
+                                          ws.data_ptr(), ws.numel(), _stream()), "uav_groupnorm_silu")
     return out
 
 
@@ -172,8 +224,9 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     if out is None:
         out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     lib = _lib.load()
-    _lib.check(lib.uav_layernorm(x.data_ptr(), rows, C, _pixel_ld(x), gamma.data_ptr(), beta.data_ptr(), eps,
-                                 out.data_ptr(), _pixel_ld(out), _stream()), "uav_layernorm")
+    with _timed("layernorm", 0.0, 2.0 * 2 * rows * C):
+        _lib.check(lib.uav_layernorm(x.data_ptr(), rows, C, _pixel_ld(x), gamma.data_ptr(), beta.data_ptr(), eps,
+                                     out.data_ptr(), _pixel_ld(out), _stream()), "uav_layernorm")
     return out
 
 
@@ -193,9 +246,10 @@ def attention(q, k, v, heads: int, *, kv_batch_div: int = 1, scale: Optional[flo
     for t in (q, k, v, out):
         assert t.dtype == torch.float16 and t.stride(-1) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
     lib = _lib.load()
-    _lib.check(lib.uav_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, d, nq, nk,
-                                 q.stride(1), k.stride(1), v.stride(1), out.stride(1), kv_batch_div, scale,
-                                 _stream()), "uav_attention")
+    with _timed("attention", 4.0 * batch * nq * nk * C, 2.0 * (2 * batch * nq * C + 2 * k.shape[0] * nk * C)):
+        _lib.check(lib.uav_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, d, nq, nk,
+                                     q.stride(1), k.stride(1), v.stride(1), out.stride(1), kv_batch_div, scale,
+                                     _stream()), "uav_attention")
     return out
 
 
@@ -208,9 +262,10 @@ def temporal_attention(q, k, v, heads: int, rot: torch.Tensor, bias: torch.Tenso
     assert rot.dtype == torch.float32 and rot.is_contiguous() and tuple(rot.shape) == (F, 16, 2)
     assert bias.dtype == torch.float32 and bias.is_contiguous() and tuple(bias.shape) == (heads, F, F)
     lib = _lib.load()
-    _lib.check(lib.uav_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, F, HW, heads, d,
-                                          _pixel_ld(q), _pixel_ld(k), _pixel_ld(v), _pixel_ld(out), d ** -0.5,
-                                          rot.data_ptr(), bias.data_ptr(), _stream()), "uav_temporal_attention")
+    with _timed("temporal_attention", 4.0 * B * HW * F * F * C, 2.0 * 4 * B * F * HW * C):
+        _lib.check(lib.uav_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, F, HW, heads, d,
+                                              _pixel_ld(q), _pixel_ld(k), _pixel_ld(v), _pixel_ld(out), d ** -0.5,
+                                              rot.data_ptr(), bias.data_ptr(), _stream()), "uav_temporal_attention")
     return out
 
 
