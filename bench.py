@@ -115,7 +115,7 @@ def cpu_baseline_sample(threads=None):
     ucfg = json.load(open(os.path.join(cfgdir, "unet_video_config.json")))
     shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "shapes_unet.json")))
     sd = make_state_dict(shapes, 1234)
-    B, T, H, W = 2, 2, 64, 96
+    B, T, H, W = 2, 1, 64, 64
     g = torch.Generator().manual_seed(0)
     sample, low = torch.randn(B, 4, T, H, W, generator=g), torch.randn(B, 3, T, H, W, generator=g)
     ctx = torch.randn(B, 77, 1024, generator=g) * 0.3

@@ -258,7 +258,11 @@ def timestep_embedding(t, dim: int, flip_sin_to_cos: bool, freq_shift: float):
     return emb
 
 
-def unet_forward(sd: SD, cfg: dict, sample, timestep, low_res, encoder_hidden_states, class_labels):
+def unet_forward(sd: SD, cfg: dict, sample, timestep, low_res, encoder_hidden_states, class_labels, taps=None):
+    """`taps` (optional dict) receives the output of every top-level stage, for stage-wise parity debugging"""
+    def _tap(name, v):
+        if taps is not None:
+            taps[name] = v
     boc = cfg["block_out_channels"]
     heads = cfg["attention_head_dim"]
     eps = cfg.get("norm_eps", 1e-5)
@@ -282,6 +286,7 @@ def unet_forward(sd: SD, cfg: dict, sample, timestep, low_res, encoder_hidden_st
         emb = emb + sd["class_embedding.weight"][class_labels.to(sample.device)].to(dtype)
 
     x = inflated_conv(sd, "conv_in", sample)
+    _tap("conv_in", x)
     skips = [x]
     for i, btype in enumerate(cfg["down_block_types"]):
         p = f"down_blocks.{i}"
@@ -295,14 +300,18 @@ def unet_forward(sd: SD, cfg: dict, sample, timestep, low_res, encoder_hidden_st
         if _has(sd, f"{p}.downsamplers.0.conv.weight"):
             x = downsample3d(sd, f"{p}.downsamplers.0", x, cfg.get("downsample_padding", 1))
             skips.append(x)
+        _tap(f"down{i}", x)
         if i in cfg["down_temporal_idx"]:
             x = temporal_module3d(sd, f"down_temp_blocks.{i}", x, emb)
+        _tap(f"down_temp{i}", x)
 
     x = resnet_block3d(sd, "mid_block.resnets.0", x, emb, eps, groups)
     x = transformer3d(sd, "mid_block.attentions.0", x, encoder_hidden_states, heads_l[-1], False, freqs, groups)
     x = resnet_block3d(sd, "mid_block.resnets.1", x, emb, eps, groups)
+    _tap("mid", x)
     if cfg["mid_temporal"]:
         x = temporal_module3d(sd, "mid_temp_block", x, emb)
+    _tap("mid_temp", x)
 
     oca_r = list(reversed(oca))
     heads_r = list(reversed(heads_l))
@@ -322,8 +331,10 @@ def unet_forward(sd: SD, cfg: dict, sample, timestep, low_res, encoder_hidden_st
                 x = transformer3d(sd, f"{p}.attentions.{j}", x, encoder_hidden_states, heads_r[i], oca_r[i], freqs, groups)
         if _has(sd, f"{p}.upsamplers.0.conv.weight"):
             x = upsample3d(sd, f"{p}.upsamplers.0", x, up_size)
+        _tap(f"up{i}", x)
         if i in cfg["up_temporal_idx"]:
             x = temporal_module3d(sd, f"up_temp_blocks.{i}", x, emb)
+        _tap(f"up_temp{i}", x)
 
     x = F.silu(group_norm(sd, "conv_norm_out", x, groups, eps))
     return inflated_conv(sd, "conv_out", x)

@@ -81,3 +81,40 @@ def test_all_gather_units_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), ROOT],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_c_abi_error_convention(uav_lib):
+    """bad arguments -> non-zero status + message, no exception / exit, nothing launched (works without a GPU)"""
+    import ctypes as C
+    from upscale_a_video_b200 import _lib
+    e = _lib.Epilogue()
+    st = uav_lib.uav_linear(None, 4, 64, 64, None, 16, None, C.byref(e), None)
+    assert st == 1 and b"null" in uav_lib.uav_last_error_string()
+    st = uav_lib.uav_conv2d(None, 1, 8, 8, 64, 64, None, 64, 5, 1, 0, None, C.byref(e), None)
+    assert st == 1 and b"ksize" in uav_lib.uav_last_error_string()
+    st = uav_lib.uav_temporal_attention(None, None, None, None, 1, 9, 4, 8, 64, 512, 512, 512, 512, 0.125, None, None, None)
+    assert st == 1
+    st = uav_lib.uav_ddim_step_v0(None, None, None, 8, 7, 1.0, 0.0, 0, 1.0, 0, None)
+    assert st == 1
+    with pytest.raises(_lib.UavError):
+        _lib.check(st, "uav_ddim_step_v0")
+    assert uav_lib.uav_launch_count() == 0
+
+
+def test_scheduler_host_tables_match_oracle():
+    """DDIMScheduler's host-side schedule (timesteps, alphas) is plain CPU math: compare with the oracle without a GPU"""
+    import json
+    from oracle import uav_oracle as O
+    from upscale_a_video_b200 import DDIMScheduler
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "meta.json")))
+    for name, kw in meta["sched_cfgs"].items():
+        a, b = DDIMScheduler(**kw), O.DDIM(**kw)
+        assert torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+        for n in (2, 30, 50):
+            a.set_timesteps(n)
+            b.set_timesteps(n)
+            assert a.timesteps.tolist() == b.timesteps.tolist() == a.timesteps_host
+        a2 = DDIMScheduler.from_config(dict(kw, _class_name="DDIMScheduler", unknown_key=1))
+        assert a2.config.prediction_type == a.config.prediction_type
+    with pytest.raises(ValueError):
+        DDIMScheduler().set_timesteps(2000)

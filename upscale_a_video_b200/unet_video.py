@@ -193,11 +193,13 @@ class UNetVideoModel(PackedModule, ConfigMixin):
             c.ctx_slices[id(m)] = (col, cc)
             col += 2 * cc
         ehs = encoder_hidden_states
-        key = ("ctx_kv", ehs.data_ptr(), ehs._version, tuple(ehs.shape), str(ehs.dtype))
-        if pk.cache.get("ctx_kv_key") != key:
+        # cache hit only for the SAME tensor object, unmodified: the cache keeps a reference to it, so its storage
+        # cannot be recycled for a different prompt while the entry is alive (a data_ptr key would go stale)
+        hit = pk.cache.get("ctx_kv_src")
+        if hit is None or hit[0] is not ehs or hit[1] != ehs._version:
             w, b = pk.fused_linear("ctx_kv_w", [x for m in cross for x in (m.to_k, m.to_v)])
             pk.cache["ctx_kv"] = ops.linear(ehs.to(torch.float16).contiguous(), w, b)
-            pk.cache["ctx_kv_key"] = key
+            pk.cache["ctx_kv_src"] = (ehs, ehs._version)
         c.ctx_kv = pk.cache["ctx_kv"]
         c.ctx_len = ehs.shape[1]
         c.rot = pk.tensor(f"rot{T}", lambda: self.temporal_rotary_emb.table(T))
@@ -249,21 +251,34 @@ class UNetVideoModel(PackedModule, ConfigMixin):
         self._prepare_ctx(c, emb, encoder_hidden_states, T)
 
         # pre-process / down / mid / up
+        taps = self.__dict__.get("_debug_taps")  # tests/debug: dict receiving every stage output (channels-last)
+
+        def _tap(name, v):
+            if taps is not None:
+                taps[name] = v
+
         x = self.conv_in.run(c, x)
+        _tap("conv_in", x)
         skips = [x]
-        for blk, tmod in zip(self.down_blocks, self.down_temp_blocks):
+        for i, (blk, tmod) in enumerate(zip(self.down_blocks, self.down_temp_blocks)):
             x, outs = blk(c, x)
             skips += outs
+            _tap(f"down{i}", x)
             x = tmod(c, x)
+            _tap(f"down_temp{i}", x)
         x = self.mid_block(c, x)
+        _tap("mid", x)
         x = self.mid_temp_block(c, x)
+        _tap("mid_temp", x)
         for i, (blk, tmod) in enumerate(zip(self.up_blocks, self.up_temp_blocks)):
             nres = len(blk.resnets)
             res, skips = skips[-nres:], skips[:-nres]
             final = i == len(self.up_blocks) - 1
             up_size = tuple(skips[-1].shape[1:4]) if (not final and forward_upsample_size) else None
             x = blk(c, x, res, up_size)
+            _tap(f"up{i}", x)
             x = tmod(c, x)
+            _tap(f"up_temp{i}", x)
         x = _gn(c, self.conv_norm_out, x, True, B)
         x = self.conv_out.run(c, x)
         out = ops.channels_last_to_planar(x, cfg.out_channels, sample.dtype if sample.dtype in
