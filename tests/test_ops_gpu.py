@@ -88,7 +88,8 @@ def _sdpa_ref(q, k, v, heads, kv_div=1):
 
 @pytest.mark.parametrize("B,heads,d,nq,nk,kv_div", [(4, 8, 128, 300, 300, 1), (6, 8, 64, 1000, 77, 3),
                                                     (2, 8, 128, 64, 77, 2), (3, 8, 64, 130, 130, 1),
-                                                    (2, 1, 512, 400, 400, 1)])
+                                                    (2, 1, 512, 400, 400, 1), (1, 1, 512, 2100, 2100, 1),
+                                                    (2, 8, 128, 1500, 1500, 1), (3, 1, 512, 130, 70, 1)])
 def test_attention(B, heads, d, nq, nk, kv_div):
     from upscale_a_video_b200 import ops
     C = heads * d
@@ -97,6 +98,10 @@ def test_attention(B, heads, d, nq, nk, kv_div):
     v = torch.randn(B // kv_div, nk, C, device="cuda").half()
     out = ops.attention(q, k, v, heads, kv_batch_div=kv_div)
     _assert_close(out, _sdpa_ref(q, k, v, heads, kv_div), 2e-3, 2e-3, f"attention d={d}")
+    # scores with a large dynamic range: exercises the lazy row-max rescaling of the tcgen05 kernel
+    q2 = (q.float() * 6).half()
+    out2 = ops.attention(q2, k, v, heads, kv_batch_div=kv_div)
+    _assert_close(out2, _sdpa_ref(q2, k, v, heads, kv_div), 4e-3, 4e-3, f"attention d={d} (peaky)")
 
 
 def test_attention_fused_qkv_slices():

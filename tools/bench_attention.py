@@ -1,0 +1,24 @@
+"""VAE-sized single-head d=512 attention and UNet d=128 self-attention: CUDA-event timing of uav_attention"""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from upscale_a_video_b200 import ops, build
+build.build()
+def timeit(fn, iters=3, warmup=1):
+    for _ in range(warmup): fn()
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+tag = "hmma" if os.environ.get("UAV_ATTENTION_HMMA") == "1" else "tcgen05"
+for name, B, heads, d, n in [("vae d512 N=46080", 1, 1, 512, 46080), ("vae d512 N=184320", 1, 1, 512, 184320),
+                             ("unet self d128 N=2880 x16 frames", 16, 8, 128, 2880)]:
+    if tag == "hmma" and n > 100000:
+        continue
+    C = heads * d
+    qkv = torch.randn(B, n, 3 * C, device="cuda").half()
+    out = torch.empty(B, n, C, device="cuda", dtype=torch.float16)
+    ms = timeit(lambda: ops.attention(qkv[..., :C], qkv[..., C:2*C], qkv[..., 2*C:], heads, out=out))
+    print(json.dumps({"impl": tag, "name": name, "ms": ms, "tflops_alg": 4.0 * B * n * n * C / ms / 1e9}))

@@ -17,6 +17,7 @@
 #include "uav_common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace uav {
 extern std::atomic<uint64_t> g_launches;
@@ -386,6 +387,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+uav_status_t attention_tc(const void* q, const void* k, const void* v, void* out, int64_t batch,
+                          int heads, int head_dim, int64_t nq, int64_t nk, int64_t ldq, int64_t ldk,
+                          int64_t ldv, int64_t ldo, int64_t kv_batch_div, float scale,
+                          cudaStream_t stream);  // attention_tc.cu (tcgen05 / TMEM)
+
 template <int DQK, int DV>
 static uav_status_t launch_fa(const FaParams& p, int batch, cudaStream_t stream) {
   constexpr int smem = (FA_BM * DQK + 2 * FA_BN * DQK + 2 * FA_BN * DV) * 2;
@@ -419,6 +425,13 @@ uav_status_t uav_attention(const void* q, const void* k, const void* v, void* ou
   UAV_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
               "uav_attention: token strides must be multiples of 8");
   UAV_REQUIRE(batch * heads <= 65535, "uav_attention: batch*heads too large");
+  UAV_REQUIRE(batch % kv_batch_div == 0, "uav_attention: batch must be a multiple of kv_batch_div");
+  // d = 128 (UNet self / cross attention at h/8) and d = 512 (VAE AttentionBlock) run on the tcgen05 / TMEM
+  // kernel; UAV_ATTENTION_HMMA=1 selects the mma.sync kernel instead (kept for A/B measurements)
+  static const bool force_hmma = getenv("UAV_ATTENTION_HMMA") != nullptr && getenv("UAV_ATTENTION_HMMA")[0] == '1';
+  if (!force_hmma && (head_dim == 128 || head_dim == 512))
+    return attention_tc(q, k, v, out, batch, heads, head_dim, nq, nk, ldq, ldk, ldv, ldo, kv_batch_div, scale,
+                        stream);
   FaParams p;
   p.q = (const __half*)q;
   p.k = (const __half*)k;

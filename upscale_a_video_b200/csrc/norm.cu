@@ -34,9 +34,9 @@ __global__ void __launch_bounds__(GN_THREADS)
   const int oct = threadIdx.x % octs;
   float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
   if (my_pix < pix_per_iter) {
-    for (int64_t p = static_cast<int64_t>(blockIdx.x) * pix_per_iter + my_pix; p < pixels;
-         p += static_cast<int64_t>(gridDim.x) * pix_per_iter) {
-      const uint4 v = ldg16(xn + p * ld + oct * 8);
+    // 4 independent 16-byte loads in flight per thread (memory-level parallelism), fixed order
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * pix_per_iter;
+    auto acc = [&](const uint4& v) {
       const __half2* h = reinterpret_cast<const __half2*>(&v);
       const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
       const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
@@ -44,7 +44,19 @@ __global__ void __launch_bounds__(GN_THREADS)
       q0 += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;
       a1 += f2.x + f2.y + f3.x + f3.y;
       q1 += f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
+    };
+    int64_t p = static_cast<int64_t>(blockIdx.x) * pix_per_iter + my_pix;
+    for (; p + 3 * stride < pixels; p += 4 * stride) {
+      const uint4 v0 = ldg16(xn + p * ld + oct * 8);
+      const uint4 v1 = ldg16(xn + (p + stride) * ld + oct * 8);
+      const uint4 v2 = ldg16(xn + (p + 2 * stride) * ld + oct * 8);
+      const uint4 v3 = ldg16(xn + (p + 3 * stride) * ld + oct * 8);
+      acc(v0);
+      acc(v1);
+      acc(v2);
+      acc(v3);
     }
+    for (; p < pixels; p += stride) acc(ldg16(xn + p * ld + oct * 8));
     s_sum[my_pix * units + oct * 2] = a0;
     s_sq[my_pix * units + oct * 2] = q0;
     s_sum[my_pix * units + oct * 2 + 1] = a1;
@@ -150,11 +162,10 @@ __global__ void __launch_bounds__(GN_THREADS)
   if ((C & 7) == 0) {
     const int octs = C >> 3;
     const int64_t total = pixels * octs;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * GN_THREADS) {
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * GN_THREADS;
+    auto one = [&](int64_t i, const uint4& v) {
       const int64_t p = i / octs;
       const int oct = static_cast<int>(i - p * octs);
-      const uint4 v = ldg16(xn + p * ld_in + oct * 8);
       const __half2* h = reinterpret_cast<const __half2*>(&v);
       uint4 o;
       uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
@@ -172,7 +183,21 @@ __global__ void __launch_bounds__(GN_THREADS)
         ow[j] = *reinterpret_cast<uint32_t*>(&r);
       }
       stg16(yn + p * ld_out + oct * 8, o);
+    };
+    auto src = [&](int64_t i) {
+      const int64_t p = i / octs;
+      return xn + p * ld_in + (i - p * octs) * 8;
+    };
+    int64_t i = static_cast<int64_t>(blockIdx.x) * GN_THREADS + threadIdx.x;
+    for (; i + 3 * gstride < total; i += 4 * gstride) {  // 4 loads in flight per thread
+      const uint4 v0 = ldg16(src(i)), v1 = ldg16(src(i + gstride));
+      const uint4 v2 = ldg16(src(i + 2 * gstride)), v3 = ldg16(src(i + 3 * gstride));
+      one(i, v0);
+      one(i + gstride, v1);
+      one(i + 2 * gstride, v2);
+      one(i + 3 * gstride, v3);
     }
+    for (; i < total; i += gstride) one(i, ldg16(src(i)));
   } else {
     const int64_t total = pixels * C;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
