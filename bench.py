@@ -106,21 +106,37 @@ def build_pipeline(device):
                                 scheduler=sched, vae=vae, unet=unet, propagator=Propagation(4, learnable=False))
 
 
+_CPU_SD = None
+
+
 def cpu_baseline_sample(threads=None):
     """the oracle (CPU port of the reference path) on a bounded sample, scaled by algorithmic FLOPs"""
     from oracle import uav_oracle as O
     from oracle.weights import make_state_dict
-    torch.set_num_threads(threads or os.cpu_count())
+    # torch's CPU kernels do not scale to every core of a 100+-core host on these small tensors: pick the fastest of a
+    # few thread counts on a tiny warm-up forward, and report the count actually used as `cores`
+    best = (None, float("inf"))
     cfgdir = os.path.join(ROOT, "upscale_a_video_b200", "configs")
     ucfg = json.load(open(os.path.join(cfgdir, "unet_video_config.json")))
     shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "shapes_unet.json")))
-    sd = make_state_dict(shapes, 1234)
+    global _CPU_SD
+    if _CPU_SD is None:
+        _CPU_SD = make_state_dict(shapes, 1234)
+    sd = _CPU_SD
     B, T, H, W = 2, 1, 64, 64
     g = torch.Generator().manual_seed(0)
     sample, low = torch.randn(B, 4, T, H, W, generator=g), torch.randn(B, 3, T, H, W, generator=g)
     ctx = torch.randn(B, 77, 1024, generator=g) * 0.3
     with torch.no_grad():
-        O.unet_forward(sd, ucfg, sample[:, :, :1, :32, :32], torch.tensor(500), low[:, :, :1, :32, :32], ctx, torch.tensor([120]))
+        cands = [threads] if threads else sorted({min(os.cpu_count(), c) for c in (8, 16, 32, 64, os.cpu_count())})
+        for nt in cands:
+            torch.set_num_threads(nt)
+            t0 = time.time()
+            O.unet_forward(sd, ucfg, sample[:, :, :1, :16, :16], torch.tensor(500), low[:, :, :1, :16, :16], ctx, torch.tensor([120]))
+            dt = time.time() - t0
+            if dt < best[1]:
+                best = (nt, dt)
+        torch.set_num_threads(best[0])
         t0 = time.time()
         O.unet_forward(sd, ucfg, sample, torch.tensor(500), low, ctx, torch.tensor([120]))
         dt = time.time() - t0

@@ -114,19 +114,28 @@ __global__ void __launch_bounds__(GN_THREADS)
   }
 }
 
-// sums[n][g] = fixed-order fp64 reduction of the per-block partials
-__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int nblocks, int G,
-                                   double* __restrict__ sums) {
+// sums[n][g] = fp64 reduction of the per-block partials in a fixed order: one warp per group, lane l takes
+// blocks l, l+32, ... then a shuffle tree (deterministic for a given launch geometry)
+__global__ void __launch_bounds__(1024)
+    gn_finalize_kernel(const float2* __restrict__ partial, int nblocks, int G,
+                       double* __restrict__ sums) {
   const int n = blockIdx.x;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
     double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = lane; b < nblocks; b += 32) {
       const float2 v = partial[(static_cast<int64_t>(n) * nblocks + b) * G + g];
       s += v.x;
       q += v.y;
     }
-    sums[(static_cast<int64_t>(n) * G + g) * 2] = s;
-    sums[(static_cast<int64_t>(n) * G + g) * 2 + 1] = q;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffff, s, o);
+      q += __shfl_xor_sync(0xffffffff, q, o);
+    }
+    if (lane == 0) {
+      sums[(static_cast<int64_t>(n) * G + g) * 2] = s;
+      sums[(static_cast<int64_t>(n) * G + g) * 2 + 1] = q;
+    }
   }
 }
 
@@ -334,7 +343,8 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
         reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, partial);
   }
   UAV_CHECK_CUDA(cudaGetLastError());
-  gn_finalize_kernel<<<(unsigned)n_outer, 64, 0, stream>>>(partial, (int)gx, groups, sums);
+  gn_finalize_kernel<<<(unsigned)n_outer, (groups >= 32 ? 1024 : 32 * groups), 0, stream>>>(partial, (int)gx, groups,
+                                                                                              sums);
   UAV_CHECK_CUDA(cudaGetLastError());
   {
     const bool vec_apply = (C % 8 == 0) && (ld_in % 8 == 0) && (ld_out % 8 == 0) &&

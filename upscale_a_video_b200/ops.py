@@ -277,8 +277,9 @@ def copy_channels(src: torch.Tensor, dst: torch.Tensor):
     C = src.shape[-1]
     assert dst.shape[-1] == C and src.numel() == dst.numel()
     lib = _lib.load()
-    _lib.check(lib.uav_copy_channels(src.data_ptr(), _pixel_ld(src), dst.data_ptr(), _pixel_ld(dst), C,
-                                     src.numel() // C, _stream()), "uav_copy_channels")
+    with _timed("copy", 0.0, 4.0 * src.numel()):
+        _lib.check(lib.uav_copy_channels(src.data_ptr(), _pixel_ld(src), dst.data_ptr(), _pixel_ld(dst), C,
+                                         src.numel() // C, _stream()), "uav_copy_channels")
     return dst
 
 
@@ -299,8 +300,9 @@ def upsample_nearest(x: torch.Tensor, size=None):
         NB *= d
     out = torch.empty(*lead, Ho, Wo, C, dtype=x.dtype, device=x.device)
     lib = _lib.load()
-    _lib.check(lib.uav_upsample_nearest(x.data_ptr(), _pixel_ld(x), NB, H, W, C, out.data_ptr(), _pixel_ld(out), Ho, Wo,
-                                        _stream()), "uav_upsample_nearest")
+    with _timed("copy", 0.0, 2.0 * (x.numel() + out.numel())):
+        _lib.check(lib.uav_upsample_nearest(x.data_ptr(), _pixel_ld(x), NB, H, W, C, out.data_ptr(), _pixel_ld(out), Ho,
+                                            Wo, _stream()), "uav_upsample_nearest")
     return out
 
 
