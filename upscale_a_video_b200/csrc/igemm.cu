@@ -18,6 +18,7 @@
 //    temporal (k,1,1) conv a (C, HW, T, B) view, Conv3d a (C, W, H, T, B) view, Linear a
 //    (K, M) view: all the same kernel, only the tensor map and the tap table differ.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -92,6 +93,7 @@ struct alignas(64) IgemmParams {
   int32_t N;      // rows of B
   int32_t n_out;  // output columns (N, or N/2 with GEGLU)
   int32_t tma_store;
+  int32_t dbg;  // development only: bit0 skip TMEM loads, bit1 skip staging stores, bit2 skip TMA store
   const float* bias;
   const __half* rowvec;
   int64_t rows_per_vec, ld_rowvec;
@@ -136,10 +138,14 @@ __device__ __forceinline__ void add_half8(float (&x)[8], const uint4& q) {
   }
 }
 
-template <int BLOCK_N, bool GEGLU>
+// TMA_EPI: smem-staged TMA-store epilogue (aligned fp16 output, >= 64-column tiles) vs per-row direct stores.
+// AUX: the epilogue has a row vector / residual / SiLU on top of the bias (compiled out otherwise: the hot
+// bias-only GEMMs get a small loop body that stays in the instruction cache).
+template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     igemm_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
+  static_assert(!TMA_EPI || Cfg::OUT_TILE_N >= 64, "TMA-store epilogue needs >= 64-column output tiles");
   constexpr int STAGES = Cfg::STAGES;
   constexpr int OUT_TILE_N = Cfg::OUT_TILE_N;
   extern __shared__ uint8_t smem_raw[];
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool tma_store = (OUT_TILE_N >= 64) && p.tma_store != 0;
+  constexpr bool tma_store = TMA_EPI;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_a);
@@ -301,8 +307,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const uint32_t taddr =
             tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
 
-        if (tma_store) {
-          if constexpr (OUT_TILE_N >= 64) {
+        if constexpr (TMA_EPI) {
+          {
             // ---- stage the bias tile, make sure the previous TMA store released the staging ----
             if (GEGLU) {
               const int j = et & (OUT_TILE_N - 1);
@@ -325,17 +331,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               const bool cols_ok = n0 < p.n_out;  // n_out % 8 == 0; groups of 8 checked below
               // issue the global loads first so their latency overlaps the TMEM load
               uint4 rq[4], vq[4];
+              if constexpr (AUX) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                rq[g] = make_uint4(0, 0, 0, 0);
-                vq[g] = make_uint4(0, 0, 0, 0);
-                if (cols_ok && n0 + g * 8 < p.n_out) {
-                  if (res != nullptr) rq[g] = ldg16(res + n0 + g * 8);
-                  if (rv != nullptr) vq[g] = ldg16(rv + n0 + g * 8);
+                for (int g = 0; g < 4; ++g) {
+                  rq[g] = make_uint4(0, 0, 0, 0);
+                  vq[g] = make_uint4(0, 0, 0, 0);
+                  if (cols_ok && n0 + g * 8 < p.n_out) {
+                    if (res != nullptr) rq[g] = ldg16(res + n0 + g * 8);
+                    if (rv != nullptr) vq[g] = ldg16(rv + n0 + g * 8);
+                  }
                 }
               }
               uint32_t a[32];
-              tmem_ld_32x32(taddr + col0, a);
+              if (!(p.dbg & 1)) tmem_ld_32x32(taddr + col0, a);
+              else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = col0 + j;
+              }
               float v[32];
               if constexpr (GEGLU) {
                 uint32_t gt[32];
@@ -350,7 +362,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               } else {
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) + sbias[col0 + j];
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 bb = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
+                  v[j4 * 4 + 0] = __uint_as_float(a[j4 * 4 + 0]) + bb.x;
+                  v[j4 * 4 + 1] = __uint_as_float(a[j4 * 4 + 1]) + bb.y;
+                  v[j4 * 4 + 2] = __uint_as_float(a[j4 * 4 + 2]) + bb.z;
+                  v[j4 * 4 + 3] = __uint_as_float(a[j4 * 4 + 3]) + bb.w;
+                }
               }
               const int slab = col0 >> 6;
               const int chunk_base = (col0 & 63) >> 3;  // 16-byte chunk index inside the 128B row
@@ -360,19 +378,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 float x[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j];
-                if (rv != nullptr) add_half8(x, vq[g]);
-                if (p.act == UAV_ACT_SILU) {
+                if constexpr (AUX) {
+                  if (rv != nullptr) add_half8(x, vq[g]);
+                  if (p.act == UAV_ACT_SILU) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+                    for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+                  }
+                  if (res != nullptr) add_half8(x, rq[g]);
                 }
-                if (res != nullptr) add_half8(x, rq[g]);
                 uint4 o;
                 o.x = pack_half2(x[0], x[1]);
                 o.y = pack_half2(x[2], x[3]);
                 o.z = pack_half2(x[4], x[5]);
                 o.w = pack_half2(x[6], x[7]);
                 const int phys = (chunk_base + g) ^ (row & 7);  // CU_TENSOR_MAP_SWIZZLE_128B
-                *reinterpret_cast<uint4*>(srow + phys * 16) = o;
+                if (!(p.dbg & 2) || o.x == 0x12345678u) *reinterpret_cast<uint4*>(srow + phys * 16) = o;
               }
             }
             // accumulator fully read: hand it back to the MMA warp
@@ -385,7 +405,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (et == 0) {
 #pragma unroll
               for (int sl = 0; sl < OUT_TILE_N / 64; ++sl) {
-                if (n_base + sl * 64 < p.n_out) {
+                if (n_base + sl * 64 < p.n_out && !(p.dbg & 4)) {
                   asm volatile(
                       "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group"
                       " [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
@@ -494,7 +514,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
       }
-      if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (TMA_EPI && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
 
@@ -527,21 +547,33 @@ struct IgemmDesc {
   const uav_epilogue_t* epi;
 };
 
-template <int BLOCK_N, bool GEGLU>
-static uav_status_t launch_instance(IgemmParams& p, cudaStream_t stream) {
+template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX>
+static uav_status_t launch_instance2(IgemmParams& p, cudaStream_t stream) {
   using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
   static bool configured = false;
   if (!configured) {
-    UAV_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, GEGLU>,
+    UAV_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, GEGLU, TMA_EPI, AUX>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     configured = true;
   }
   const uint32_t grid = p.num_tiles < (uint32_t)num_sms() ? p.num_tiles : (uint32_t)num_sms();
-  igemm_kernel<BLOCK_N, GEGLU><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  igemm_kernel<BLOCK_N, GEGLU, TMA_EPI, AUX><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   UAV_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return UAV_OK;
+}
+
+template <int BLOCK_N, bool GEGLU>
+static uav_status_t launch_instance(IgemmParams& p, cudaStream_t stream) {
+  const bool aux = p.rowvec != nullptr || p.residual != nullptr || p.act == UAV_ACT_SILU;
+  if constexpr (IgemmCfg<BLOCK_N, GEGLU>::OUT_TILE_N >= 64) {
+    if (p.tma_store) {
+      return aux ? launch_instance2<BLOCK_N, GEGLU, true, true>(p, stream)
+                 : launch_instance2<BLOCK_N, GEGLU, true, false>(p, stream);
+    }
+  }
+  return launch_instance2<BLOCK_N, GEGLU, false, true>(p, stream);
 }
 
 static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
@@ -649,6 +681,10 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
                        (p.residual == nullptr || (p.ld_res % 8 == 0 && aligned16(p.residual))) &&
                        (p.rowvec == nullptr || (p.ld_rowvec % 8 == 0 && aligned16(p.rowvec)));
   p.tma_store = can_tma ? 1 : 0;
+  {
+    const char* dbg = getenv("UAV_IGEMM_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
+  }
   if (can_tma) {
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};

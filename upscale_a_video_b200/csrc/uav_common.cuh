@@ -211,7 +211,8 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t ab_fmt, uint32_t M, u
 }
 
 // ---- misc math ----
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// fast division (<= 2 ulp): keeps the IEEE-division slow path (and its code size) out of every epilogue
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
