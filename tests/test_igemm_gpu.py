@@ -145,3 +145,36 @@ def test_conv3d(B, T, H, W, Cin, Cout):
     out = ops.conv3d(x, w, b)
     ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float().permute(0, 4, 1, 2, 3), b, padding=1)
     _close(out, ref.permute(0, 2, 3, 4, 1), Cin * 27, "conv3d")
+
+
+# ---- two-CTA cluster / weight-multicast path (needs >= 2 * num_SMs M-tiles); odd tile counts exercise the ghost tile
+@pytest.mark.parametrize("M,K,N,act", [(299 * 128 - 3, 512, 512, 0), (300 * 128, 320, 128, 0), (301 * 128 + 7, 512, 2048, 2),
+                                       (298 * 128, 1024, 384, 1)])
+def test_linear_cluster(M, K, N, act):
+    from upscale_a_video_b200 import ops
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    b = torch.randn(N, device="cuda") * 0.1
+    res = torch.randn(M, N // 2 if act == 2 else N, device="cuda").half() if act != 2 else None
+    out = ops.linear(a, w, b, act=act, residual=res)
+    y = a.float() @ w.float().t() + b
+    if act == 2:
+        h, g = y.chunk(2, dim=-1)
+        ref = h * F.gelu(g)
+    elif act == 1:
+        ref = F.silu(y) + res.float()
+    else:
+        ref = y + res.float()
+    _close(out, ref, K, f"cluster linear {M}x{K}x{N} act{act}")
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,k,stride", [(5, 96, 160, 128, 256, 3, 1), (3, 128, 208, 64, 128, 3, 1),
+                                                      (7, 160, 144, 64, 256, 3, 2), (2, 168, 232, 256, 512, 1, 1)])
+def test_conv2d_cluster(NB, H, W, Cin, Cout, k, stride):
+    from upscale_a_video_b200 import ops
+    x = torch.randn(NB, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, k, k, Cin, device="cuda") * 0.05).half()
+    b = torch.randn(Cout, device="cuda")
+    out = ops.conv2d(x, w, b, stride=stride)
+    ref = _conv_ref(x, w, b, stride, k // 2)
+    _close(out, ref, Cin * k * k, f"cluster conv2d {NB}x{H}x{W} {Cin}->{Cout} k{k} s{stride}")

@@ -90,6 +90,8 @@ struct alignas(64) IgemmParams {
   uint32_t tiles[5];     // tiles along dims 1..4
   uint32_t out_dims[5];  // output extents along dims 1..4
   uint32_t n_tiles, num_tiles;
+  int32_t stages_a, stages_b;  // depth of the activation / weight smem rings (runtime split of the same smem)
+  uint32_t num_pairs;  // cluster mode: ceil(m_tiles / 2) * n_tiles work items, two M-tiles each
   int32_t N;      // rows of B
   int32_t n_out;  // output columns (N, or N/2 with GEGLU)
   int32_t tma_store;
@@ -111,14 +113,16 @@ struct IgemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_BYTES = (OUT_TILE_N >= 64) ? (OUT_TILE_N / 64) * SLAB_BYTES : 0;
   static constexpr int AUX_BYTES = 2048;  // barriers + tmem slot + bias tile (256 floats)
-  static constexpr int STAGES_RAW = (232448 - 1024 - STAGING_BYTES - AUX_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  // everything left of the 227 KB after the output staging tile is one region shared by the A and B rings
+  static constexpr int RING_BYTES = ((232448 - 1024 - STAGING_BYTES - AUX_BYTES) / 1024) * 1024;
+  static constexpr int STAGES_RAW = RING_BYTES / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;  // balanced depth
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
                                    : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256
                                                           : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + AUX_BYTES + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + AUX_BYTES + 1024 /*align*/;
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -141,7 +145,11 @@ __device__ __forceinline__ void add_half8(float (&x)[8], const uint4& q) {
 // TMA_EPI: smem-staged TMA-store epilogue (aligned fp16 output, >= 64-column tiles) vs per-row direct stores.
 // AUX: the epilogue has a row vector / residual / SiLU on top of the bias (compiled out otherwise: the hot
 // bias-only GEMMs get a small loop body that stays in the instruction cache).
-template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX>
+// CL: 1 = independent CTAs; 2 = clusters of two CTAs working on two M-tiles of the same N-tile: each CTA
+// fetches HALF of the shared weight tile and multicasts it into both CTAs' shared memory, which cuts the
+// L2->SM weight traffic in half (the K <= 1024 GEMMs of the transformer blocks are L2-bandwidth bound with
+// 128 x 256 tiles: the 256 x K weight tile is twice the 128 x K activation tile).
+template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     igemm_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
@@ -152,16 +160,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   // 1024-byte alignment (SWIZZLE_128B atoms) in the shared address space
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  // two independent rings in the same RING_BYTES region: activations (A) come from HBM on the
+  // K <= 1024 GEMMs and need more bytes in flight than the weight tiles (B), which are L2 hits
+  const int SA = p.stages_a, SB = p.stages_b;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* smem_b = smem + SA * A_STAGE_BYTES;
+  uint8_t* staging = smem + Cfg::RING_BYTES;
   uint8_t* aux = staging + Cfg::STAGING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
-  uint64_t* full_bar = bars;                     // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  constexpr int MAXS = 10;
+  uint64_t* fulla_bar = bars;                     // [MAXS]
+  uint64_t* emptya_bar = bars + MAXS;             // [MAXS]
+  uint64_t* fullb_bar = bars + 2 * MAXS;          // [MAXS]
+  uint64_t* emptyb_bar = bars + 3 * MAXS;         // [MAXS]
+  uint64_t* tfull_bar = bars + 4 * MAXS;          // [2]
+  uint64_t* tempty_bar = bars + 4 * MAXS + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAXS + 4);
   float* sbias = reinterpret_cast<float*>(aux + 512);  // [BLOCK_N]
 
   const int warp_idx = threadIdx.x >> 5;
@@ -174,9 +188,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (tma_store) tma_prefetch_desc(&p.map_out);
   }
   if (warp_idx == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&fulla_bar[s], 1);
+      mbar_init(&emptya_bar[s], 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(&fullb_bar[s], 1);
+      mbar_init(&emptyb_bar[s], CL);  // freed when every CTA the stage's B half was multicast to has consumed it
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
@@ -189,19 +207,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // peer barriers are initialised before any multicast lands in them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = p.num_taps * p.kblocks_per_tap;
+  // work items: a tile (CL == 1) or a pair of M-tiles sharing one N-tile (CL == 2)
+  const uint32_t cta_rank = (CL == 2) ? cluster_ctarank() : 0u;
+  const uint32_t work0 = (CL == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const uint32_t work_stride = (CL == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const uint32_t num_work = (CL == 2) ? p.num_pairs : p.num_tiles;
 
   if (warp_idx == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const uint32_t n_tile = tile % p.n_tiles;
-        uint32_t idx = tile / p.n_tiles;
+      for (uint32_t w = work0; w < num_work; w += work_stride) {
+        const uint32_t n_tile = w % p.n_tiles;
+        uint32_t idx = (w / p.n_tiles) * CL + cta_rank;  // M-tile (may be a ghost tile past the end: all OOB)
         const int c1 = (idx % p.tiles[1]) * p.box[1];
         idx /= p.tiles[1];
         const int c2 = (idx % p.tiles[2]) * p.box[2];
@@ -213,20 +237,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const int o0 = p.tap_off[tap][0], o1 = p.tap_off[tap][1], o2 = p.tap_off[tap][2],
                     o3 = p.tap_off[tap][3], o4 = p.tap_off[tap][4];
           for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_5d(&p.map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES,
+            mbar_wait(&emptya_bar[stage], phase ^ 1);
+            mbar_expect_tx(&fulla_bar[stage], A_STAGE_BYTES);
+            tma_load_5d(&p.map_a, &fulla_bar[stage], smem_a + stage * A_STAGE_BYTES,
                         kc * BLOCK_K + o0, c1 + o1, c2 + o2, c3 + o3, c4 + o4);
+            if (++stage == SA) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 3) {
+    // =============================== TMA producer: weights ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint32_t w = work0; w < num_work; w += work_stride) {
+        const uint32_t n_tile = w % p.n_tiles;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
+            mbar_wait(&emptyb_bar[stage], phase ^ 1);
+            mbar_expect_tx(&fullb_bar[stage], Cfg::B_STAGE_BYTES);
             const int kcoord = tap * p.k_per_tap + kc * BLOCK_K;
             uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-            if (GEGLU) {
-              tma_load_2d(&p.map_b, &full_bar[stage], sb, kcoord, n_tile * (BLOCK_N / 2));
-              tma_load_2d(&p.map_b, &full_bar[stage], sb + Cfg::B_STAGE_BYTES / 2, kcoord,
+            if (CL == 2) {
+              // this CTA's half of the weight tile, delivered to both CTAs (GEGLU: rank 0 = value rows, 1 = gate rows)
+              const int brow = GEGLU ? (cta_rank == 0 ? n_tile * (BLOCK_N / 2) : p.N / 2 + n_tile * (BLOCK_N / 2))
+                                     : (n_tile * BLOCK_N + cta_rank * (BLOCK_N / 2));
+              tma_load_2d_mc(&p.map_b, &fullb_bar[stage], sb + cta_rank * (Cfg::B_STAGE_BYTES / 2), kcoord, brow,
+                             (uint16_t)3);
+            } else if (GEGLU) {
+              tma_load_2d(&p.map_b, &fullb_bar[stage], sb, kcoord, n_tile * (BLOCK_N / 2));
+              tma_load_2d(&p.map_b, &fullb_bar[stage], sb + Cfg::B_STAGE_BYTES / 2, kcoord,
                           p.N / 2 + n_tile * (BLOCK_N / 2));
             } else {
-              tma_load_2d(&p.map_b, &full_bar[stage], sb, kcoord, n_tile * BLOCK_N);
+              tma_load_2d(&p.map_b, &fullb_bar[stage], sb, kcoord, n_tile * BLOCK_N);
             }
-            if (++stage == STAGES) {
+            if (++stage == SB) {
               stage = 0;
               phase ^= 1;
             }
@@ -238,29 +287,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(0 /*f16*/, BLOCK_M, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (uint32_t w = work0; w < num_work; w += work_stride, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&fulla_bar[sa], pha);
+          mbar_wait(&fullb_bar[sb], phb);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + sa * A_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + sb * Cfg::B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements = 32 bytes along K inside the 128B swizzle row: +2 (>>4)
             umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit(&emptya_bar[sa]);
+          if (CL == 2) umma_commit_mc(&emptyb_bar[sb], (uint16_t)3);
+          else umma_commit(&emptyb_bar[sb]);
           if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          if (++sa == SA) {
+            sa = 0;
+            pha ^= 1;
+          }
+          if (++sb == SB) {
+            sb = 0;
+            phb ^= 1;
           }
         }
       }
@@ -281,10 +337,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t l4 = r;
     if (tma_store || half == 0) {
       uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (uint32_t w = work0; w < num_work; w += work_stride, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        const uint32_t n_tile = tile % p.n_tiles;
-        uint32_t idx = tile / p.n_tiles;
+        const uint32_t n_tile = w % p.n_tiles;
+        uint32_t idx = (w / p.n_tiles) * CL + cta_rank;
         const uint32_t t1 = (idx % p.tiles[1]) * p.box[1];
         idx /= p.tiles[1];
         const uint32_t t2 = (idx % p.tiles[2]) * p.box[2];
@@ -521,6 +577,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   // teardown
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -547,33 +604,57 @@ struct IgemmDesc {
   const uav_epilogue_t* epi;
 };
 
-template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX>
-static uav_status_t launch_instance2(IgemmParams& p, cudaStream_t stream) {
+template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX, int CL>
+static uav_status_t launch_instance3(IgemmParams& p, cudaStream_t stream) {
   using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
   static bool configured = false;
+  auto kern = igemm_kernel<BLOCK_N, GEGLU, TMA_EPI, AUX, CL>;
   if (!configured) {
-    UAV_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, GEGLU, TMA_EPI, AUX>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::SMEM_BYTES));
+    UAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const uint32_t grid = p.num_tiles < (uint32_t)num_sms() ? p.num_tiles : (uint32_t)num_sms();
-  igemm_kernel<BLOCK_N, GEGLU, TMA_EPI, AUX><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
-  UAV_CHECK_CUDA(cudaGetLastError());
+  const uint32_t sms = (uint32_t)num_sms();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (CL == 2) {
+    const uint32_t clusters = p.num_pairs < sms / 2 ? p.num_pairs : sms / 2;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(p.num_tiles < sms ? p.num_tiles : sms);
+  }
+  UAV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return UAV_OK;
 }
 
+template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX>
+static uav_status_t launch_instance2(IgemmParams& p, bool cluster, cudaStream_t stream) {
+  if constexpr (BLOCK_N >= 128) {
+    if (cluster) return launch_instance3<BLOCK_N, GEGLU, TMA_EPI, AUX, 2>(p, stream);
+  }
+  return launch_instance3<BLOCK_N, GEGLU, TMA_EPI, AUX, 1>(p, stream);
+}
+
 template <int BLOCK_N, bool GEGLU>
-static uav_status_t launch_instance(IgemmParams& p, cudaStream_t stream) {
+static uav_status_t launch_instance(IgemmParams& p, bool cluster, cudaStream_t stream) {
   const bool aux = p.rowvec != nullptr || p.residual != nullptr || p.act == UAV_ACT_SILU;
   if constexpr (IgemmCfg<BLOCK_N, GEGLU>::OUT_TILE_N >= 64) {
     if (p.tma_store) {
-      return aux ? launch_instance2<BLOCK_N, GEGLU, true, true>(p, stream)
-                 : launch_instance2<BLOCK_N, GEGLU, true, false>(p, stream);
+      return aux ? launch_instance2<BLOCK_N, GEGLU, true, true>(p, cluster, stream)
+                 : launch_instance2<BLOCK_N, GEGLU, true, false>(p, cluster, stream);
     }
   }
-  return launch_instance2<BLOCK_N, GEGLU, false, true>(p, stream);
+  return launch_instance2<BLOCK_N, GEGLU, false, true>(p, cluster, stream);
 }
 
 static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
@@ -601,6 +682,12 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   else if (d.N > 16) block_n = 32;
   else block_n = 16;
 
+  // two-CTA clusters (weight-tile multicast) when there are enough M-tiles to keep every SM busy
+  uint64_t m_tiles_pre = 1;
+  for (int i = 1; i < 5; ++i) m_tiles_pre *= d.tiles[i];
+  static const bool cluster_enabled = !(getenv("UAV_IGEMM_CLUSTER") && getenv("UAV_IGEMM_CLUSTER")[0] == '0');
+  const bool use_cluster = cluster_enabled && block_n >= 128 && m_tiles_pre >= 2ull * (uint64_t)num_sms();
+
   // A map
   {
     cuuint64_t dims[5], strides[4];
@@ -614,9 +701,15 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
       strides[i - 1] = d.a_strides[i] * 2;
       UAV_REQUIRE(strides[i - 1] % 16 == 0, "igemm: A stride %d not 16-byte aligned", i);
     }
+    // L2 promotion 256B: a 128-byte k-block fetch also brings the neighbouring 128 bytes of the row into L2, i.e. the
+    // next k-block of the same rows (half the DRAM transactions, better page locality for the streaming GEMMs)
+    static const int promo = getenv("UAV_IGEMM_A_PROMO") ? atoi(getenv("UAV_IGEMM_A_PROMO")) : 256;
     CUresult r = encode(&p.map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d.a),
                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_SWIZZLE_128B,
+                        promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                     : (promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                    : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UAV_REQUIRE(r == CUDA_SUCCESS, "igemm: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
@@ -625,7 +718,8 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d.N};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(geglu ? block_n / 2 : block_n)};
+    // cluster mode: each CTA of a pair fetches (and multicasts) half of the weight tile
+    cuuint32_t box[2] = {64, (cuuint32_t)((geglu || use_cluster) ? block_n / 2 : block_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&p.map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d.w), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -656,6 +750,27 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   p.n_tiles = (uint32_t)((p.n_out + out_tile_n - 1) / out_tile_n);
   UAV_REQUIRE(m_tiles * p.n_tiles < (1ull << 31), "igemm: too many tiles");
   p.num_tiles = (uint32_t)(m_tiles * p.n_tiles);
+  p.num_pairs = (uint32_t)(((m_tiles + 1) / 2) * p.n_tiles);
+  {
+    // ring split inside the fixed RING_BYTES region.  Convolutions re-read their activation tiles from L2
+    // (9 taps) -> balanced rings.  Single-tap GEMMs stream activations from HBM (high latency) against L2-resident
+    // weights -> deep A ring, shallow B ring.
+    const int b_stage = block_n * BLOCK_K * 2;
+    const int staging = out_tile_n >= 64 ? (out_tile_n / 64) * SLAB_BYTES : 0;
+    const int ring = ((232448 - 1024 - staging - 2048) / 1024) * 1024;  // == IgemmCfg::RING_BYTES
+    int sb = ring / (A_STAGE_BYTES + b_stage);  // balanced depth
+    if (sb > 8) sb = 8;
+    int sa = sb;
+    // measured on B200: no gain (the weight ring becomes the limiter) -> opt-in only
+    static const bool deep_a = getenv("UAV_IGEMM_DEEP_A") && getenv("UAV_IGEMM_DEEP_A")[0] == '1';
+    if (deep_a && d.num_taps == 1 && sb > 2) {
+      sb = 2;
+      sa = (ring - sb * b_stage) / A_STAGE_BYTES;
+      if (sa > 10) sa = 10;
+    }
+    p.stages_a = sa;
+    p.stages_b = sb;
+  }
   p.bias = e->bias;
   p.rowvec = reinterpret_cast<const __half*>(e->rowvec);
   p.rows_per_vec = e->rows_per_vec > 0 ? e->rows_per_vec : 1;
@@ -703,13 +818,13 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
     UAV_REQUIRE(r == CUDA_SUCCESS, "igemm: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
   }
 
-  if (geglu) return launch_instance<256, true>(p, stream);
+  if (geglu) return launch_instance<256, true>(p, use_cluster, stream);
   switch (block_n) {
-    case 256: return launch_instance<256, false>(p, stream);
-    case 128: return launch_instance<128, false>(p, stream);
-    case 64: return launch_instance<64, false>(p, stream);
-    case 32: return launch_instance<32, false>(p, stream);
-    default: return launch_instance<16, false>(p, stream);
+    case 256: return launch_instance<256, false>(p, use_cluster, stream);
+    case 128: return launch_instance<128, false>(p, use_cluster, stream);
+    case 64: return launch_instance<64, false>(p, false, stream);
+    case 32: return launch_instance<32, false>(p, false, stream);
+    default: return launch_instance<16, false>(p, false, stream);
   }
 }
 
