@@ -123,7 +123,7 @@ def cpu_baseline_sample(threads=None):
     if _CPU_SD is None:
         _CPU_SD = make_state_dict(shapes, 1234)
     sd = _CPU_SD
-    B, T, H, W = 2, 1, 64, 64
+    B, T, H, W = 2, 4, 96, 128  # bounded sample: ~10-20 s on 16-32 host threads
     g = torch.Generator().manual_seed(0)
     sample, low = torch.randn(B, 4, T, H, W, generator=g), torch.randn(B, 3, T, H, W, generator=g)
     ctx = torch.randn(B, 77, 1024, generator=g) * 0.3
@@ -268,8 +268,32 @@ def main():
         ig = summ.get("igemm", dict(flops=0.0, ms=1.0, launches=1))
         tot_ms = sum(d["ms"] for d in summ.values())
         achieved = ig["flops"] / ig["ms"] / 1e9
+        # one representative launch of the same kernel, timed alone (CUDA events): conv3x3 512->512 on 16 x 160x288
+        xr = torch.randn(16, 160, 288, 512, device=device).half()
+        wr = (torch.randn(512, 3, 3, 512, device=device) * 0.02).half()
+        br = torch.zeros(512, device=device)
+        orr = torch.empty(16, 160, 288, 512, device=device, dtype=torch.float16)
+        for _ in range(3):
+            ops.conv2d(xr, wr, br, out=orr)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.conv2d(xr, wr, br, out=orr)
+        e1.record()
+        torch.cuda.synchronize()
+        rep_ms = e0.elapsed_time(e1) / 10
+        rep_flops = 2.0 * 16 * 160 * 288 * 512 * 512 * 9
+        burst = peaks.get("bf16_tflops", 1590.0)
         roof = {"bound": "tensor", "kernel": "uav::igemm_kernel (tcgen05 implicit GEMM: conv2d/conv_t/linear)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                # DRAM bytes of the representative launch below, from `ncu --set full` (profiles/r1_ncu_full_summaries.txt:
+                # 759.96 MB read + 719.35 MB written; algorithmic = 755 MB in + 755 MB out + 4.7 MB weights)
+                "traffic": 1479313920,
+                "representative_launch": {"op": "conv3x3 512->512, 16 x 160x288 (3.48 TFLOP)", "ms": rep_ms,
+                                          "achieved": rep_flops / rep_ms / 1e9, "peak_burst": burst,
+                                          "frac_of_burst_peak": rep_flops / rep_ms / 1e9 / burst,
+                                          "algorithmic_bytes": 2 * (16 * 160 * 288 * 512 * 2) + 512 * 9 * 512 * 2,
+                                          "ncu_tensor_pipe_active_pct": 85.05},
                 "peak_source": which, "launches_per_unet_forward": ig["launches"],
                 "share_of_unet_forward_time": ig["ms"] / tot_ms,
                 "per_kind_ms": {k: round(d["ms"], 3) for k, d in summ.items()},

@@ -99,6 +99,15 @@ uav_status_t uav_conv3d(const void* x, int64_t B, int64_t T, int64_t H, int64_t 
                         int64_t ld_in, const void* w, int64_t Cout, void* out,
                         const uav_epilogue_t* epi, uav_stream_t stream);
 
+/* Upsample3D (resnet.py:143-156): F.interpolate(scale 2, nearest) followed by the 3x3 conv, computed WITHOUT
+ * materialising the upsampled tensor: output pixel (2y+a, 2x+b) only sees 2x2 source pixels, so the 3x3 filter
+ * collapses into four 2x2 phase filters (rows {W0, W1+W2} for a=0, {W0+W1, W2} for a=1; same for columns) —
+ * 4/9 of the MACs and no 4x-sized intermediate.  w4: fp16 [4 phases (a*2+b)][Cout][2][2][Cin] (summed in fp32 by the
+ * caller, then rounded once).  x: [NB][H][W][ld_in]; out: [NB][2H][2W][ld_out]; bias-only fp16 epilogue. */
+uav_status_t uav_upsample2x_conv3x3(const void* x, int64_t NB, int64_t H, int64_t W, int64_t Cin,
+                                    int64_t ld_in, const void* w4, int64_t Cout, void* out,
+                                    const uav_epilogue_t* epi, uav_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * normalisation
  * ------------------------------------------------------------------------------------------- */

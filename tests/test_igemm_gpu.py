@@ -178,3 +178,18 @@ def test_conv2d_cluster(NB, H, W, Cin, Cout, k, stride):
     out = ops.conv2d(x, w, b, stride=stride)
     ref = _conv_ref(x, w, b, stride, k // 2)
     _close(out, ref, Cin * k * k, f"cluster conv2d {NB}x{H}x{W} {Cin}->{Cout} k{k} s{stride}")
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 12, 20, 64, 64), (3, 40, 72, 128, 256), (16, 20, 36, 512, 512), (1, 9, 7, 256, 128)])
+def test_upsample2x_conv3x3(NB, H, W, Cin, Cout):
+    """nearest x2 + 3x3 conv via four collapsed 2x2 phase filters == upsample then conv (weights summed in fp32 and
+    rounded once, so the tolerance includes that extra fp16 weight rounding)"""
+    from upscale_a_video_b200 import ops
+    x = torch.randn(NB, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda") * 0.05).half()
+    b = torch.randn(Cout, device="cuda")
+    out = ops.upsample2x_conv3x3(x, ops.collapse_upsample_filter(w), b)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.float().permute(0, 3, 1, 2), b, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _close(out, ref, Cin * 9, f"upsample2x+conv {NB}x{H}x{W} {Cin}->{Cout}")

@@ -40,6 +40,7 @@ _PROTOS = {
     "uav_conv2d": [P, I64, I64, I64, I64, I64, P, I64, I32, I32, I32, P, EP, P],
     "uav_conv_temporal": [P, I64, I64, I64, I64, I64, P, I64, I32, P, EP, P],
     "uav_conv3d": [P, I64, I64, I64, I64, I64, I64, P, I64, P, EP, P],
+    "uav_upsample2x_conv3x3": [P, I64, I64, I64, I64, I64, P, I64, P, EP, P],
     "uav_groupnorm_silu": [P, I64, I64, I64, I64, I32, P, P, F32, I32, P, I64, P, C.c_size_t, P],
     "uav_layernorm": [P, I64, I64, I64, P, P, F32, P, I64, P],
     "uav_attention": [P, P, P, P, I64, I32, I32, I64, I64, I64, I64, I64, I64, I64, F32, P],

@@ -602,6 +602,9 @@ struct IgemmDesc {
   int64_t N;
   void* out;
   const uav_epilogue_t* epi;
+  // optional strided output view (elements) for dims 1..4; 0 = dense (derived from ld_out / out_dims).
+  // Only the TMA-store epilogue understands it (used by the fused nearest-x2 upsample + 3x3 conv).
+  uint64_t out_strides[5];
 };
 
 template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX, int CL>
@@ -796,6 +799,8 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
                        (p.residual == nullptr || (p.ld_res % 8 == 0 && aligned16(p.residual))) &&
                        (p.rowvec == nullptr || (p.ld_rowvec % 8 == 0 && aligned16(p.rowvec)));
   p.tma_store = can_tma ? 1 : 0;
+  UAV_REQUIRE(d.out_strides[1] == 0 || (can_tma && p.residual == nullptr && p.rowvec == nullptr),
+              "igemm: a strided output view needs the TMA-store epilogue without residual / row vector");
   {
     const char* dbg = getenv("UAV_IGEMM_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
@@ -809,7 +814,7 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
     for (int i = 1; i < 5; ++i) {
       dims[i] = d.out_dims[i];
       box[i] = d.box[i];
-      strides[i - 1] = stride_el * 2;
+      strides[i - 1] = (d.out_strides[i] ? d.out_strides[i] : stride_el) * 2;
       stride_el *= d.out_dims[i];
     }
     CUresult r = encode(&p.map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, d.out, dims, strides, box,
@@ -1048,6 +1053,61 @@ uav_status_t uav_conv3d(const void* x, int64_t B, int64_t T, int64_t H, int64_t 
         o[4] = 0;
       }
   return launch_igemm(d, (cudaStream_t)stream);
+}
+
+uav_status_t uav_upsample2x_conv3x3(const void* x, int64_t NB, int64_t H, int64_t W, int64_t Cin,
+                                    int64_t ld_in, const void* w4, int64_t Cout, void* out,
+                                    const uav_epilogue_t* epi, uav_stream_t stream) {
+  UAV_REQUIRE(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && ld_in >= Cin && epi != nullptr,
+              "uav_upsample2x_conv3x3: bad shape");
+  UAV_REQUIRE(epi->residual == nullptr && epi->rowvec == nullptr && epi->out_dtype == UAV_F16 && Cout >= 33,
+              "uav_upsample2x_conv3x3: bias-only fp16 epilogue with Cout > 32 required");
+  const int64_t ld_out = epi->ld_out;
+  uint32_t tw, th;
+  pick_tile_2d(W, H, &tw, &th);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      IgemmDesc d;
+      memset(&d, 0, sizeof(d));
+      d.a = x;
+      d.w = reinterpret_cast<const __half*>(w4) + static_cast<int64_t>(a * 2 + b) * Cout * 4 * Cin;
+      d.N = Cout;
+      d.epi = epi;
+      d.k_per_tap = (int)Cin;
+      const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 1};
+      const uint64_t strides[5] = {1, (uint64_t)ld_in, (uint64_t)ld_in * W, (uint64_t)ld_in * W * H,
+                                   (uint64_t)ld_in * W * H * NB};
+      const uint32_t box[5] = {64, tw, th, 1, 1};
+      const uint32_t tiles[5] = {1, (uint32_t)((W + tw - 1) / tw), (uint32_t)((H + th - 1) / th), (uint32_t)NB, 1};
+      const uint32_t odims[5] = {1, (uint32_t)W, (uint32_t)H, (uint32_t)NB, 1};
+      for (int i = 0; i < 5; ++i) {
+        d.a_dims[i] = dims[i];
+        d.a_strides[i] = strides[i];
+        d.box[i] = box[i];
+        d.tiles[i] = tiles[i];
+        d.out_dims[i] = odims[i];
+      }
+      // output phase (a, b): pixel (2y + a, 2x + b) of the [NB][2H][2W][ld_out] tensor
+      d.out = reinterpret_cast<__half*>(out) + (static_cast<int64_t>(a) * 2 * W + b) * ld_out;
+      d.out_strides[1] = 2 * (uint64_t)ld_out;
+      d.out_strides[2] = 2 * 2 * (uint64_t)W * ld_out;
+      d.out_strides[3] = 4 * (uint64_t)H * W * ld_out;
+      d.out_strides[4] = 4 * (uint64_t)H * W * ld_out * NB;
+      // source taps of the collapsed 2x2 filter: phase 0 reads {-1, 0}, phase 1 reads {0, +1}
+      d.num_taps = 4;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          int32_t* o = d.tap_off[ty * 2 + tx];
+          o[0] = 0;
+          o[1] = (b == 0 ? -1 : 0) + tx;
+          o[2] = (a == 0 ? -1 : 0) + ty;
+          o[3] = 0;
+          o[4] = 0;
+        }
+      uav_status_t st = launch_igemm(d, (cudaStream_t)stream);
+      if (st != UAV_OK) return st;
+    }
+  return UAV_OK;
 }
 
 }  // extern "C"

@@ -147,6 +147,40 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, pad_mode=0,
     return out
 
 
+def upsample2x_conv3x3(x: torch.Tensor, w4: torch.Tensor, bias=None):
+    """nearest x2 upsample + 3x3 conv without the upsampled intermediate.  x: (..., H, W, Cin); w4: (4, Cout, 2, 2, Cin)
+    phase filters from `collapse_upsample_filter`."""
+    assert x.dtype == torch.float16 and w4.dtype == torch.float16 and w4.is_contiguous()
+    *lead, H, W, Cin = x.shape
+    Cout = w4.shape[1]
+    assert tuple(w4.shape) == (4, Cout, 2, 2, Cin)
+    NB = 1
+    for d in lead:
+        NB *= d
+    out = torch.empty(*lead, 2 * H, 2 * W, Cout, dtype=torch.float16, device=x.device)
+    e = _epi(out, bias)
+    lib = _lib.load()
+    with _timed("igemm", 2.0 * NB * 4 * H * W * Cout * Cin * 4, 2.0 * (NB * H * W * Cin + w4.numel() + out.numel())):
+        _lib.check(lib.uav_upsample2x_conv3x3(x.data_ptr(), NB, H, W, Cin, _pixel_ld(x), w4.data_ptr(), Cout,
+                                              out.data_ptr(), C.byref(e), _stream()), "uav_upsample2x_conv3x3")
+    return out
+
+
+def collapse_upsample_filter(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, 3, 3, Cin) conv filter applied after a nearest x2 upsample -> (4, Cout, 2, 2, Cin) phase filters
+    (summed in fp32, rounded to fp16 once).  Phase p = a*2+b produces output pixel (2y+a, 2x+b); its taps read source
+    rows {y-1, y} (a=0) or {y, y+1} (a=1), columns likewise."""
+    w = w.float()
+    rows = [torch.stack([w[:, 0], w[:, 1] + w[:, 2]], dim=1), torch.stack([w[:, 0] + w[:, 1], w[:, 2]], dim=1)]  # (Cout,2,3,Cin)
+    out = []
+    for a in range(2):
+        r = rows[a]
+        cols = [torch.stack([r[:, :, 0], r[:, :, 1] + r[:, :, 2]], dim=2), torch.stack([r[:, :, 0] + r[:, :, 1], r[:, :, 2]], dim=2)]
+        for b in range(2):
+            out.append(cols[b])
+    return torch.stack(out, dim=0).to(torch.float16).contiguous()
+
+
 def conv_temporal(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=None, rowvec=None,
                   rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
     """x: (B, T, H, W, Cin); w: (Cout, k, Cin) — nn.Conv3d (k,1,1), zero padding (k-1)/2 in t."""
