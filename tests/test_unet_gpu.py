@@ -52,3 +52,19 @@ def test_unet_forward_vs_golden(unet, case):
     # second call (cached prompt K/V, packed weights) must be bit-identical
     out2 = m(sample, torch.tensor(c["timestep"]), low, encoder_hidden_states=ctx, class_labels=c["class_labels"].cuda()).sample
     assert torch.equal(out, out2)
+
+
+def test_unet_shared_cfg_prefix(unet):
+    """cfg_shared_input=True (prefix computed once for both CFG halves) == the plain batch-2 forward up to fp16
+    reduction-order noise (GroupNorm partial sums are grouped differently for batch 1 and 2)"""
+    m, sd, cfg = unet
+    c = torch.load(os.path.join(G, "unet.pt"), weights_only=False)["t3_16x24"]
+    sample = c["sample"][:1].repeat(2, 1, 1, 1, 1).cuda().half()
+    low = c["low_res"][:1].repeat(2, 1, 1, 1, 1).cuda().half()
+    ctx = c["ctx"].cuda().half()
+    a = m(sample, 601, low, encoder_hidden_states=ctx, class_labels=torch.tensor([120])).sample
+    b = m(sample, 601, low, encoder_hidden_states=ctx, class_labels=torch.tensor([120]), cfg_shared_input=True).sample
+    err = _rel(b, a)
+    print(f"\n[unet shared-prefix] rel L2 diff vs unshared {err:.3e}")
+    assert err < 2e-3
+    assert not torch.equal(a[0], a[1])  # the two halves differ (different text rows)

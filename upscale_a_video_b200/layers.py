@@ -530,11 +530,15 @@ class DownBlock3D(nn.Module):
         self.downsamplers = (nn.ModuleList([Downsample3D(out_channels, True, out_channels, downsample_padding, "op")])
                              if add_downsample else None)
 
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, expand_batch_to: int = 0):
+        """`expand_batch_to`: the input is the text-independent prefix computed for ONE classifier-free-guidance half;
+        it is broadcast to the full batch right before the first text-dependent op (the first Transformer3DModel)."""
         outs = []
         for i, r in enumerate(self.resnets):
             x = r(c, x)
             if self.attentions is not None:
+                if expand_batch_to and x.shape[0] != expand_batch_to:
+                    x = ops.repeat_batch(x, expand_batch_to)
                 x = self.attentions[i](c, x)
             outs.append(x)
         if self.downsamplers is not None:

@@ -37,10 +37,22 @@ class Profile:
     def __exit__(self, *a):
         Profile.active = None
 
+    def by_tag(self):
+        """per (kind, tag) totals: launches, flops, ms — for finding the expensive shapes"""
+        torch.cuda.synchronize()
+        out = {}
+        for kind, fl, by, s, e, tag in self.records:
+            d = out.setdefault((kind, tag), dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+            d["ms"] += s.elapsed_time(e)
+        return out
+
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for kind, fl, by, s, e in self.records:
+        for kind, fl, by, s, e, _tag in self.records:
             d = out.setdefault(kind, dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
             d["launches"] += 1
             d["flops"] += fl
@@ -50,10 +62,10 @@ class Profile:
 
 
 class _timed:
-    __slots__ = ("kind", "flops", "bytes", "s")
+    __slots__ = ("kind", "flops", "bytes", "s", "tag")
 
-    def __init__(self, kind, flops=0.0, nbytes=0.0):
-        self.kind, self.flops, self.bytes = kind, flops, nbytes
+    def __init__(self, kind, flops=0.0, nbytes=0.0, tag=""):
+        self.kind, self.flops, self.bytes, self.tag = kind, flops, nbytes, tag
 
     def __enter__(self):
         if Profile.active is not None:
@@ -65,7 +77,7 @@ class _timed:
         if p is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
-            p.records.append((self.kind, self.flops, self.bytes, self.s, e))
+            p.records.append((self.kind, self.flops, self.bytes, self.s, e, self.tag))
 
 
 def _pixel_ld(x: torch.Tensor) -> int:
@@ -118,7 +130,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     assert out.shape[-1] == n_out and out.numel() // n_out == M
     e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
     lib = _lib.load()
-    with _timed("igemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out)):
+    with _timed("igemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out), f"linear M{M} K{K} N{N} act{act}"):
         _lib.check(lib.uav_linear(a.data_ptr(), M, K, _pixel_ld(a) if a.dim() > 1 else K, w.data_ptr(), N,
                                   out.data_ptr(), C.byref(e), _stream()), "uav_linear")
     return out
@@ -141,7 +153,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, pad_mode=0,
     e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
     lib = _lib.load()
     with _timed("igemm", 2.0 * NB * Ho * Wo * Cout * Cin * k * k,
-                2.0 * (NB * H * W * Cin + w.numel()) + out.element_size() * NB * Ho * Wo * Cout):
+                2.0 * (NB * H * W * Cin + w.numel()) + out.element_size() * NB * Ho * Wo * Cout,
+                f"conv{k}x{k}s{stride} {NB}x{H}x{W} {Cin}->{Cout}"):
         _lib.check(lib.uav_conv2d(x.data_ptr(), NB, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k, stride,
                                   pad_mode, out.data_ptr(), C.byref(e), _stream()), "uav_conv2d")
     return out
@@ -160,7 +173,8 @@ def upsample2x_conv3x3(x: torch.Tensor, w4: torch.Tensor, bias=None):
     out = torch.empty(*lead, 2 * H, 2 * W, Cout, dtype=torch.float16, device=x.device)
     e = _epi(out, bias)
     lib = _lib.load()
-    with _timed("igemm", 2.0 * NB * 4 * H * W * Cout * Cin * 4, 2.0 * (NB * H * W * Cin + w4.numel() + out.numel())):
+    with _timed("igemm", 2.0 * NB * 4 * H * W * Cout * Cin * 4, 2.0 * (NB * H * W * Cin + w4.numel() + out.numel()),
+                f"up2x+conv {NB}x{H}x{W} {Cin}->{Cout}"):
         _lib.check(lib.uav_upsample2x_conv3x3(x.data_ptr(), NB, H, W, Cin, _pixel_ld(x), w4.data_ptr(), Cout,
                                               out.data_ptr(), C.byref(e), _stream()), "uav_upsample2x_conv3x3")
     return out
@@ -192,7 +206,8 @@ def conv_temporal(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, resi
         out = torch.empty(B, T, H, W, Cout, dtype=out_dtype, device=x.device)
     e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
     lib = _lib.load()
-    with _timed("igemm", 2.0 * B * T * H * W * Cout * Cin * k, 2.0 * (x.numel() + w.numel() + B * T * H * W * Cout)):
+    with _timed("igemm", 2.0 * B * T * H * W * Cout * Cin * k, 2.0 * (x.numel() + w.numel() + B * T * H * W * Cout),
+                f"conv_t{k} {B}x{T}x{H}x{W} {Cin}->{Cout}"):
         _lib.check(lib.uav_conv_temporal(x.data_ptr(), B, T, H * W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k,
                                          out.data_ptr(), C.byref(e), _stream()), "uav_conv_temporal")
     return out
@@ -244,7 +259,7 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     lib = _lib.load()
     nbytes = lib.uav_groupnorm_workspace_bytes(n_outer, groups)
     ws = _gn_workspace(x.device, nbytes)
-    with _timed("groupnorm", 0.0, 2.0 * 3 * total_pix * C):  # read (stats) + read + write
+    with _timed("groupnorm", 0.0, 2.0 * 3 * total_pix * C, f"gn {total_pix}px C{C}"):  # read (stats) + read + write
         _lib.check(lib.uav_groupnorm_silu(x.data_ptr(), n_outer, pixels, C, _pixel_ld(x), groups, gamma.data_ptr(),
                                           beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), _pixel_ld(out),
                                           ws.data_ptr(), ws.numel(), _stream()), "uav_groupnorm_silu")
@@ -280,7 +295,8 @@ def attention(q, k, v, heads: int, *, kv_batch_div: int = 1, scale: Optional[flo
     for t in (q, k, v, out):
         assert t.dtype == torch.float16 and t.stride(-1) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
     lib = _lib.load()
-    with _timed("attention", 4.0 * batch * nq * nk * C, 2.0 * (2 * batch * nq * C + 2 * k.shape[0] * nk * C)):
+    with _timed("attention", 4.0 * batch * nq * nk * C, 2.0 * (2 * batch * nq * C + 2 * k.shape[0] * nk * C),
+                f"attn b{batch} h{heads} d{d} nq{nq} nk{nk}"):
         _lib.check(lib.uav_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, d, nq, nk,
                                      q.stride(1), k.stride(1), v.stride(1), out.stride(1), kv_batch_div, scale,
                                      _stream()), "uav_attention")
@@ -318,10 +334,24 @@ def copy_channels(src: torch.Tensor, dst: torch.Tensor):
 
 
 def concat_channels(a: torch.Tensor, b: torch.Tensor):
-    """torch.cat([a, b], dim=channel) for channels-last tensors"""
+    """torch.cat([a, b], dim=channel) for channels-last tensors.  `b` may have batch 1 while `a` has batch > 1 (a skip
+    connection computed once for both classifier-free-guidance halves): it is then broadcast over the batch."""
     out = torch.empty(*a.shape[:-1], a.shape[-1] + b.shape[-1], dtype=a.dtype, device=a.device)
     copy_channels(a, out[..., : a.shape[-1]])
-    copy_channels(b, out[..., a.shape[-1]:])
+    if b.shape[0] == 1 and a.shape[0] > 1:
+        for i in range(a.shape[0]):
+            copy_channels(b, out[i:i + 1, ..., a.shape[-1]:])
+    else:
+        copy_channels(b, out[..., a.shape[-1]:])
+    return out
+
+
+def repeat_batch(x: torch.Tensor, n: int):
+    """x (1, ...) -> (n, ...) by copy (channels-last)"""
+    assert x.shape[0] == 1
+    out = torch.empty(n, *x.shape[1:], dtype=x.dtype, device=x.device)
+    for i in range(n):
+        copy_channels(x, out[i:i + 1])
     return out
 
 

@@ -225,6 +225,11 @@ class VideoUpscalePipeline(ConfigMixin):
         if use_prop:
             ff, fb = flows_bi[0].to(latents).contiguous(), flows_bi[1].to(latents).contiguous()
 
+        # both CFG halves see the same latents / LR frames / noise level: our UNet computes the text-independent prefix once
+        shared = {}
+        if do_cfg and num_images_per_prompt == 1 and batch_size == 1 and \
+                "cfg_shared_input" in inspect.signature(self.unet.forward).parameters:
+            shared = {"cfg_shared_input": True}
         windows = sharding.unet_windows(T)
         uniq = sharding.unique(windows)
         for i, t in enumerate(timesteps):
@@ -234,7 +239,7 @@ class VideoUpscalePipeline(ConfigMixin):
                 for ui, (s, e) in enumerate(uniq):
                     if ui % world == rank:
                         local[ui] = self.unet(lat_in[:, :, s:e], t, image[:, :, s:e], encoder_hidden_states=prompt_embeds,
-                                              class_labels=denoise_level_t).sample
+                                              class_labels=denoise_level_t, **shared).sample
                 outs = sharding.all_gather_units(local, len(uniq), (lat_in.shape[0], C_lat, sharding.SHORT_SEQ, H, W),
                                                  dtype, device, self.process_group)
                 noise_pred = torch.empty(lat_in.shape[0], C_lat, T, H, W, dtype=dtype, device=device)
@@ -246,7 +251,8 @@ class VideoUpscalePipeline(ConfigMixin):
                         covered[s + k] = True
                     ops.window_blend(noise_pred, outs[uniq.index((s, e))].contiguous(), s, mask)
             else:
-                noise_pred = self.unet(lat_in, t, image, encoder_hidden_states=prompt_embeds, class_labels=noise_level_t).sample
+                noise_pred = self.unet(lat_in, t, image, encoder_hidden_states=prompt_embeds, class_labels=noise_level_t,
+                                       **shared).sample
             if do_cfg:
                 noise_pred = ops.cfg_combine(noise_pred.contiguous(), float(guidance_scale))
             x0 = self.scheduler.step_v0(noise_pred, t, latents, **extra).pred_original_sample
