@@ -89,7 +89,8 @@ def _sdpa_ref(q, k, v, heads, kv_div=1):
 @pytest.mark.parametrize("B,heads,d,nq,nk,kv_div", [(4, 8, 128, 300, 300, 1), (6, 8, 64, 1000, 77, 3),
                                                     (2, 8, 128, 64, 77, 2), (3, 8, 64, 130, 130, 1),
                                                     (2, 1, 512, 400, 400, 1), (1, 1, 512, 2100, 2100, 1),
-                                                    (2, 8, 128, 1500, 1500, 1), (3, 1, 512, 130, 70, 1)])
+                                                    (2, 8, 128, 1500, 1500, 1), (3, 1, 512, 130, 70, 1),
+                                                    (4, 8, 128, 2000, 77, 2), (2, 8, 64, 777, 100, 1), (8, 8, 64, 5000, 77, 4)])
 def test_attention(B, heads, d, nq, nk, kv_div):
     from upscale_a_video_b200 import ops
     C = heads * d

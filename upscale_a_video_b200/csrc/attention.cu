@@ -252,6 +252,176 @@ __global__ void __launch_bounds__(FA_THREADS)
 }
 
 // ---------------------------------------------------------------------------------------
+// text cross-attention (nk <= 128, typically 77): K and V of one (batch, head) stay resident in
+// shared memory, the CTA streams query tiles past them (double-buffered cp.async), the whole
+// score row fits in registers (single-pass softmax), and each warp stages its 16 output rows in
+// the Q buffer it has just consumed.  The generic kernel above spends most of its time in the
+// per-CTA prologue / epilogue when there are only two KV tiles (measured 1.0 TB/s at h/2).
+// ---------------------------------------------------------------------------------------
+template <int D, int NB16>
+__global__ void __launch_bounds__(FA_THREADS)
+    cross_attn_kernel(const FaParams p) {
+  constexpr int NKP = NB16 * 16;
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  __half* sk = reinterpret_cast<__half*>(fa_smem);   // [NKP][D]
+  __half* sv = sk + NKP * D;                          // [NKP][D]
+  __half* sq = sv + NKP * D;                          // [2][64][D]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads, h = bh % p.heads;
+  const __half* qg = p.q + b * p.bsq + static_cast<int64_t>(h) * D;
+  const __half* kg = p.k + (b / p.kv_batch_div) * p.bsk + static_cast<int64_t>(h) * D;
+  const __half* vg = p.v + (b / p.kv_batch_div) * p.bsv + static_cast<int64_t>(h) * D;
+  __half* og = p.o + b * p.bso + static_cast<int64_t>(h) * D;
+  constexpr int QC = D / 8;
+  const int ntiles = (p.nq + FA_BM - 1) / FA_BM;
+
+  for (int i = tid; i < NKP * QC; i += FA_THREADS) {
+    const int r = i / QC, c = i % QC;
+    const bool ok = r < p.nk;
+    cp_async16(tile_ptr<D>(sk, r, c), kg + static_cast<int64_t>(ok ? r : 0) * p.ldk + c * 8, ok);
+    cp_async16(tile_ptr<D>(sv, r, c), vg + static_cast<int64_t>(ok ? r : 0) * p.ldv + c * 8, ok);
+  }
+  auto load_q = [&](int tile, int buf) {
+    const int q0 = tile * FA_BM;
+    __half* sqb = sq + buf * FA_BM * D;
+    for (int i = tid; i < FA_BM * QC; i += FA_THREADS) {
+      const int r = i / QC, c = i % QC;
+      const bool ok = q0 + r < p.nq;
+      cp_async16(tile_ptr<D>(sqb, r, c), qg + static_cast<int64_t>(ok ? q0 + r : 0) * p.ldq + c * 8, ok);
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) load_q(tile, 0);
+  cp_async_commit();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int arow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int achk = lane >> 4;
+  int it = 0;
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) load_q(next, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    __half* sqb = sq + buf * FA_BM * D;
+
+    // S = Q K^T  (16 x NKP per warp)
+    float s[NB16 * 2][4];
+#pragma unroll
+    for (int i = 0; i < NB16 * 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      uint32_t a[4];
+      ldmatrix_x4(a, tile_ptr<D>(sqb, arow, kk * 2 + achk));
+#pragma unroll
+      for (int nb = 0; nb < NB16; ++nb) {
+        uint32_t bfr[4];
+        const int brow = nb * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int bchk = kk * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(bfr, tile_ptr<D>(sk, brow, bchk));
+        mma16816(s[nb * 2], a, bfr[0], bfr[1]);
+        mma16816(s[nb * 2 + 1], a, bfr[2], bfr[3]);
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nb = 0; nb < NB16 * 2; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nb * 8 + t4 * 2 + (e & 1);
+        float x = s[nb][e] * p.scale_log2;
+        if (col >= p.nk) x = -INFINITY;
+        s[nb][e] = x;
+        mx[e >> 1] = fmaxf(mx[e >> 1], x);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffff, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffff, mx[r], 2));
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[NB16 * 2][2];
+#pragma unroll
+    for (int nb = 0; nb < NB16 * 2; ++nb) {
+      const float p0 = exp2f(s[nb][0] - mx[0]), p1 = exp2f(s[nb][1] - mx[0]);
+      const float p2 = exp2f(s[nb][2] - mx[1]), p3 = exp2f(s[nb][3] - mx[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+      pf[nb][0] = *reinterpret_cast<uint32_t*>(&h01);
+      pf[nb][1] = *reinterpret_cast<uint32_t*>(&h23);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffff, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffff, rs[r], 2);
+      rs[r] = 1.f / rs[r];
+    }
+    // O = P V
+    float o_acc[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NB16; ++kk) {
+      const uint32_t a[4] = {pf[kk * 2][0], pf[kk * 2][1], pf[kk * 2 + 1][0], pf[kk * 2 + 1][1]};
+#pragma unroll
+      for (int nb = 0; nb < D / 16; ++nb) {
+        uint32_t bfr[4];
+        const int vrow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int vchk = nb * 2 + (lane >> 4);
+        ldmatrix_x4_trans(bfr, tile_ptr<D>(sv, vrow, vchk));
+        mma16816(o_acc[nb * 2], a, bfr[0], bfr[1]);
+        mma16816(o_acc[nb * 2 + 1], a, bfr[2], bfr[3]);
+      }
+    }
+    // stage this warp's 16 rows in its own (already consumed) rows of the Q buffer, then 16-byte stores
+    __syncwarp();
+#pragma unroll
+    for (int nb = 0; nb < D / 8; ++nb) {
+      const int r0 = warp * 16 + g, r1 = r0 + 8;
+      __half2 v0 = __floats2half2_rn(o_acc[nb][0] * rs[0], o_acc[nb][1] * rs[0]);
+      __half2 v1 = __floats2half2_rn(o_acc[nb][2] * rs[1], o_acc[nb][3] * rs[1]);
+      *reinterpret_cast<__half2*>(tile_ptr<D>(sqb, r0, nb) + t4 * 2) = v0;
+      *reinterpret_cast<__half2*>(tile_ptr<D>(sqb, r1, nb) + t4 * 2) = v1;
+    }
+    __syncwarp();
+    const int q0 = tile * FA_BM;
+    for (int i = lane; i < 16 * QC; i += 32) {
+      const int r = warp * 16 + i / QC, c = i % QC;
+      if (q0 + r < p.nq)
+        stg16(og + static_cast<int64_t>(q0 + r) * p.ldo + c * 8,
+              *reinterpret_cast<const uint4*>(tile_ptr<D>(sqb, r, c)));
+    }
+    __syncthreads();  // buffer `buf` is refilled by the prefetch issued in the next iteration
+  }
+  cp_async_wait<0>();
+}
+
+template <int D, int NB16>
+static uav_status_t launch_cross(const FaParams& p, int batch, cudaStream_t stream) {
+  constexpr int smem = (2 * NB16 * 16 * D + 2 * FA_BM * D) * 2;
+  static bool configured = false;
+  if (!configured) {
+    UAV_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_kernel<D, NB16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int ntiles = (p.nq + FA_BM - 1) / FA_BM;
+  // enough CTAs to fill the GPU ~4x over, each streaming several query tiles past its resident K/V
+  int gx = (num_sms() * 8 + batch * p.heads - 1) / (batch * p.heads);
+  if (gx > ntiles) gx = ntiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, batch * p.heads);
+  cross_attn_kernel<D, NB16><<<grid, FA_THREADS, smem, stream>>>(p);
+  UAV_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return UAV_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // temporal attention: one warp per (batch, pixel, head); lane = frame * 4 + quarter
 // ---------------------------------------------------------------------------------------
 struct TaParams {
@@ -428,6 +598,18 @@ uav_status_t uav_attention(const void* q, const void* k, const void* v, void* ou
   UAV_REQUIRE(batch % kv_batch_div == 0, "uav_attention: batch must be a multiple of kv_batch_div");
   // d = 128 (UNet self / cross attention at h/8) and d = 512 (VAE AttentionBlock) run on the tcgen05 / TMEM
   // kernel; UAV_ATTENTION_HMMA=1 selects the mma.sync kernel instead (kept for A/B measurements)
+  static const bool no_cross = getenv("UAV_ATTENTION_NOCROSS") != nullptr && getenv("UAV_ATTENTION_NOCROSS")[0] == '1';
+  if (!no_cross && nk <= 128 && nq >= 4 * nk && (head_dim == 64 || head_dim == 128)) {
+    // short key/value sequence (the 77 prompt tokens): resident-KV streaming kernel
+    FaParams pc;
+    pc.q = (const __half*)q; pc.k = (const __half*)k; pc.v = (const __half*)v; pc.o = (__half*)out;
+    pc.ldq = ldq; pc.ldk = ldk; pc.ldv = ldv; pc.ldo = ldo;
+    pc.bsq = nq * ldq; pc.bsk = nk * ldk; pc.bsv = nk * ldv; pc.bso = nq * ldo;
+    pc.nq = (int)nq; pc.nk = (int)nk; pc.heads = heads; pc.kv_batch_div = (int)kv_batch_div;
+    pc.scale_log2 = scale * 1.4426950408889634f;
+    if (head_dim == 64) return nk <= 80 ? launch_cross<64, 5>(pc, (int)batch, stream) : launch_cross<64, 8>(pc, (int)batch, stream);
+    return nk <= 80 ? launch_cross<128, 5>(pc, (int)batch, stream) : launch_cross<128, 8>(pc, (int)batch, stream);
+  }
   static const bool force_hmma = getenv("UAV_ATTENTION_HMMA") != nullptr && getenv("UAV_ATTENTION_HMMA")[0] == '1';
   if (!force_hmma && (head_dim == 128 || head_dim == 512))
     return attention_tc(q, k, v, out, batch, heads, head_dim, nq, nk, ldq, ldk, ldv, ldo, kv_batch_div, scale,
