@@ -84,3 +84,72 @@ def test_pipeline_vs_golden(unet, vaes, case):
     print(f"\n[pipeline {case}] rel L2 err: latents {e_lat:.3e}, frames {e_img:.3e}")
     assert e_lat < 5e-2 and e_img < 5e-2
     assert out.min().item() >= -1.0 and out.max().item() <= 1.0
+
+
+def test_pipeline_multiwindow_vs_oracle(unet, vaes):
+    """T = 16: windows (0,8),(6,14),(8,16) -> frames 8..13 are covered by two or three windows, so the order-dependent
+    0.5/0.5 blend (pipeline_upscale_a_video.py:630-634) and the window sharding plan are exercised.  Reference = the oracle
+    pipeline in fp32 on the host (same weights / inputs / noise draws)."""
+    import bench
+    from oracle import uav_oracle as O
+    from oracle.weights import make_state_dict
+    from upscale_a_video_b200 import DDIMScheduler, DDPMScheduler, Propagation, VideoUpscalePipeline
+    T, H, W, steps = 16, 16, 16, 2
+    image, fw, bw, pe = bench.synth_inputs(T, H, W, "cpu")
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(1, 3, T, H, W, generator=g)
+    lat0 = torch.randn(1, 4, T, H, W, generator=g)
+    scfg = META["sched_cfgs"]["v_scaled_offset"]
+    pipe = VideoUpscalePipeline(None, None, DDPMScheduler(beta_schedule="scaled_linear"), DDIMScheduler(**scfg), vaes["vae_3d"],
+                                unet, Propagation(4, learnable=False))
+    neg, pos = pe.half().cuda().chunk(2)
+    out, lat = pipe(None, image=image.cuda(), flows_bi=[fw.cuda(), bw.cuda()], num_inference_steps=steps, guidance_scale=6.0,
+                    noise_level=120, prompt_embeds=pos, negative_prompt_embeds=neg, latents=lat0.cuda(), noise=noise.cuda(),
+                    propagation_steps=[1], return_dict=False)
+    ucfg = json.load(open(os.path.join(CFG, "unet_video_config.json")))
+    vcfg = json.load(open(os.path.join(CFG, "vae_3d_config.json")))
+    usd = make_state_dict(json.load(open(os.path.join(G, "shapes_unet.json"))), META["seed_unet"])
+    vsd = make_state_dict(json.load(open(os.path.join(G, "shapes_vae_3d.json"))), META["seed_vae"])
+    with torch.no_grad():
+        ref, ref_lat = O.pipeline_call(usd, ucfg, vsd, vcfg, O.DDIM(**scfg), O.DDIM(beta_schedule="scaled_linear"), image=image,
+                                       prompt_embeds=pe, noise=noise, latents=lat0, flows_bi=[fw, bw],
+                                       num_inference_steps=steps, guidance_scale=6.0, noise_level=120, propagation_steps=[1],
+                                       return_latents=True)
+    e_lat, e_img = _rel(lat, ref_lat), _rel(out, ref)
+    print(f"\n[pipeline T=16 multi-window] rel L2 err vs fp32 oracle: latents {e_lat:.3e}, frames {e_img:.3e}")
+    assert e_lat < 5e-2 and e_img < 5e-2
+
+
+def test_pipeline_fp32_working_dtype(unet, vaes):
+    """fp32 prompt embeddings make the whole sampler run in fp32 tensors (the UNet still computes in fp16 internally)"""
+    from upscale_a_video_b200 import DDIMScheduler, DDPMScheduler, Propagation, VideoUpscalePipeline
+    c = torch.load(os.path.join(G, "pipeline.pt"), weights_only=False)["c1_t1_64x64"]
+    pipe = VideoUpscalePipeline(None, None, DDPMScheduler(beta_schedule="scaled_linear"),
+                                DDIMScheduler(**META["sched_cfgs"]["v_scaled_offset"]), vaes[c["vae"]], unet,
+                                Propagation(4, learnable=False))
+    neg, pos = c["prompt_embeds"].cuda().float().chunk(2)
+    out, lat = pipe(None, image=c["image"].cuda(), num_inference_steps=c["steps"], guidance_scale=c["guidance_scale"],
+                    noise_level=c["noise_level"], prompt_embeds=pos, negative_prompt_embeds=neg, latents=c["latents"].cuda(),
+                    noise=c["noise"].cuda(), return_dict=False)
+    assert lat.dtype == torch.float32
+    e_lat, e_img = _rel(lat, c["latents_out"]), _rel(out, c["out"])
+    print(f"\n[pipeline c1 fp32 sampler] rel L2 err: latents {e_lat:.3e}, frames {e_img:.3e}")
+    assert e_lat < 3e-2 and e_img < 3e-2
+
+
+def test_pipeline_input_validation(unet, vaes):
+    """error conventions of the reference (pipeline_upscale_a_video.py:365-418, 512, 581-588)"""
+    from upscale_a_video_b200 import DDIMScheduler, DDPMScheduler, VideoUpscalePipeline
+    pipe = VideoUpscalePipeline(None, None, DDPMScheduler(), DDIMScheduler(), vaes["vae_3d"], unet, None)
+    img = torch.zeros(1, 3, 1, 16, 16, device="cuda")
+    emb = torch.zeros(1, 77, 1024, device="cuda", dtype=torch.float16)
+    with pytest.raises(ValueError):
+        pipe(None, image=img)  # neither prompt nor prompt_embeds
+    with pytest.raises(ValueError):
+        pipe("a", image=img, prompt_embeds=emb)  # both
+    with pytest.raises(ValueError):
+        pipe(None, image=img, prompt_embeds=emb, negative_prompt_embeds=emb, noise_level=351)  # > max_noise_level
+    with pytest.raises(ValueError):
+        pipe(None, image=torch.zeros(2, 3, 1, 16, 16, device="cuda"), prompt_embeds=emb, negative_prompt_embeds=emb)
+    with pytest.raises(ValueError):
+        pipe(None, image=img, prompt_embeds=emb, negative_prompt_embeds=emb, latents=torch.zeros(1, 4, 2, 16, 16))
