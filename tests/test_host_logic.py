@@ -118,3 +118,27 @@ def test_scheduler_host_tables_match_oracle():
         assert a2.config.prediction_type == a.config.prediction_type
     with pytest.raises(ValueError):
         DDIMScheduler().set_timesteps(2000)
+
+
+def test_tile_plan_matches_reference_loop():
+    """tests/golden/tiles.json was minted by executing the reference's own tile loop (oracle/make_golden_tiles.py)"""
+    import json
+    from upscale_a_video_b200.tiling import needs_tiling, plan_tiles
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "tiles.json")))
+    assert len(cases) >= 20
+    for c in cases:
+        plan = plan_tiles(c["h"], c["w"], c["tile_size"])
+        assert [list(t.in_box) for t in plan] == c["tiles_in"], (c["h"], c["w"], c["tile_size"])
+        # replay the paste with a nearest-x4 "pipeline": must reproduce what the reference loop produced
+        h, w = c["h"], c["w"]
+        frame = torch.arange(h * w, dtype=torch.float32).reshape(1, 1, 1, h, w)
+        out = torch.zeros(1, 1, 1, 4 * h, 4 * w)
+        for t in plan:
+            y0, y1, x0, x1 = t.in_box
+            up = frame[..., y0:y1, x0:x1].repeat_interleave(4, -2).repeat_interleave(4, -1)
+            oy0, oy1, ox0, ox1 = t.out_box
+            sy0, sy1, sx0, sx1 = t.src_box
+            out[..., oy0:oy1, ox0:ox1] = up[..., sy0:sy1, sx0:sx1]
+        exact = torch.equal(out, frame.repeat_interleave(4, -2).repeat_interleave(4, -1))
+        assert exact == c["paste_exact"], (h, w, c["tile_size"])
+    assert needs_tiling(320, 576) and not needs_tiling(180, 320)
