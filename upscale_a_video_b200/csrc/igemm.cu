@@ -95,7 +95,6 @@ struct alignas(64) IgemmParams {
   int32_t N;      // rows of B
   int32_t n_out;  // output columns (N, or N/2 with GEGLU)
   int32_t tma_store;
-  int32_t dbg;  // development only: bit0 skip TMEM loads, bit1 skip staging stores, bit2 skip TMA store
   const float* bias;
   const __half* rowvec;
   int64_t rows_per_vec, ld_rowvec;
@@ -399,11 +398,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
               }
               uint32_t a[32];
-              if (!(p.dbg & 1)) tmem_ld_32x32(taddr + col0, a);
-              else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = col0 + j;
-              }
+              tmem_ld_32x32(taddr + col0, a);
               float v[32];
               if constexpr (GEGLU) {
                 uint32_t gt[32];
@@ -448,7 +443,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 o.z = pack_half2(x[4], x[5]);
                 o.w = pack_half2(x[6], x[7]);
                 const int phys = (chunk_base + g) ^ (row & 7);  // CU_TENSOR_MAP_SWIZZLE_128B
-                if (!(p.dbg & 2) || o.x == 0x12345678u) *reinterpret_cast<uint4*>(srow + phys * 16) = o;
+                *reinterpret_cast<uint4*>(srow + phys * 16) = o;
               }
             }
             // accumulator fully read: hand it back to the MMA warp
@@ -461,7 +456,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (et == 0) {
 #pragma unroll
               for (int sl = 0; sl < OUT_TILE_N / 64; ++sl) {
-                if (n_base + sl * 64 < p.n_out && !(p.dbg & 4)) {
+                if (n_base + sl * 64 < p.n_out) {
                   asm volatile(
                       "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group"
                       " [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
@@ -801,10 +796,6 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   p.tma_store = can_tma ? 1 : 0;
   UAV_REQUIRE(d.out_strides[1] == 0 || (can_tma && p.residual == nullptr && p.rowvec == nullptr),
               "igemm: a strided output view needs the TMA-store epilogue without residual / row vector");
-  {
-    const char* dbg = getenv("UAV_IGEMM_DBG");
-    p.dbg = dbg ? atoi(dbg) : 0;
-  }
   if (can_tma) {
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
