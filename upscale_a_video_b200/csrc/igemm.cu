@@ -9,11 +9,15 @@
 //    zero fill outside the image = the convolution's zero padding) lands directly in the
 //    128B-swizzled K-major layout tcgen05.mma consumes — no im2col buffer, no layout copies
 //    (the reference pays two permute copies per conv: resnet.py:97-99).
-//  * persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA
-//    issuer (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16),
-//    warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/temb/act/residual ->
-//    16B stores).  Two TMEM accumulators so the epilogue of tile i overlaps the main loop of
-//    tile i+1; a STAGES-deep smem ring of {A 128x64, B BLOCK_Nx64} fp16 tiles.
+//  * persistent CTAs (one per SM), warp-specialised: warp 0 = activation TMA producer, warp 3 = weight TMA
+//    producer, warp 1 = MMA issuer (single thread), warp 2 = TMEM allocator, warps 4-11 = epilogue
+//    (tcgen05.ld -> bias/temb/act/residual -> swizzled smem staging -> TMA store).  Two TMEM accumulators so
+//    the epilogue of tile i overlaps the main loop of tile i+1; smem rings of {A 128x64, B BLOCK_Nx64} fp16 tiles.
+//  * large launches (>= 2 M-tiles per SM, BLOCK_N >= 128) run as CTA PAIRS: tcgen05.mma.cta_group::2 with
+//    M=256 across the two SMs of a TPC, each CTA holding its 128 activation rows and half of the weight tile
+//    (5 x 32 KB stages instead of 3 x 48 KB; half the L2->SM weight traffic).  Measured on B200 (interleaved,
+//    thermally settled): +12..29 % on the single-tap GEMMs (Linear 512->512 / 512->1536 / 2048->512, temporal
+//    conv), parity on the MMA-bound 3x3 convs.  Smaller launches use cta_group::1 (M=128).
 //  * stride-2 convs read a 5-D "phase" view (2C, W/2, 2, H/2, NB) of the same buffer, the
 //    temporal (k,1,1) conv a (C, HW, T, B) view, Conv3d a (C, W, H, T, B) view, Linear a
 //    (K, M) view: all the same kernel, only the tensor map and the tap table differ.
@@ -144,10 +148,14 @@ __device__ __forceinline__ void add_half8(float (&x)[8], const uint4& q) {
 // TMA_EPI: smem-staged TMA-store epilogue (aligned fp16 output, >= 64-column tiles) vs per-row direct stores.
 // AUX: the epilogue has a row vector / residual / SiLU on top of the bias (compiled out otherwise: the hot
 // bias-only GEMMs get a small loop body that stays in the instruction cache).
-// CL: 1 = independent CTAs; 2 = clusters of two CTAs working on two M-tiles of the same N-tile: each CTA
-// fetches HALF of the shared weight tile and multicasts it into both CTAs' shared memory, which cuts the
-// L2->SM weight traffic in half (the K <= 1024 GEMMs of the transformer blocks are L2-bandwidth bound with
-// 128 x 256 tiles: the 256 x K weight tile is twice the 128 x K activation tile).
+// CL: 1 = independent CTAs; 2 = CTA pairs (tcgen05 cta_group::2) computing a 256 x BLOCK_N tile: each CTA holds its
+// own 128 activation rows and HALF of the weight tile (rows [rank * BLOCK_N/2, +BLOCK_N/2)); the leader (rank 0) issues
+// M=256 MMAs that read both CTAs' shared memory and write both CTAs' tensor memory.  A weight stage shrinks to half
+// (deeper rings in the same shared memory: 5 x 32 KB instead of 3 x 48 KB at BLOCK_N = 256, which is what hides the
+// HBM latency of the single-tap GEMMs) and the L2->SM weight traffic halves.  Barrier protocol: the full barriers
+// live in the leader (both producers arrive.expect_tx on them and both CTAs' TMA loads complete_tx there), the empty /
+// accumulator-full barriers are per CTA and signalled by multicast commits, the accumulator-empty barrier lives in the
+// leader and collects the epilogue warps of both CTAs.
 template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     igemm_kernel(const __grid_constant__ IgemmParams p) {
@@ -164,6 +172,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const int SA = p.stages_a, SB = p.stages_b;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + SA * A_STAGE_BYTES;
+  constexpr int B_STAGE = Cfg::B_STAGE_BYTES / CL;  // bytes of one weight stage in THIS CTA
   uint8_t* staging = smem + Cfg::RING_BYTES;
   uint8_t* aux = staging + Cfg::STAGING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
@@ -188,25 +197,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < SA; ++s) {
-      mbar_init(&fulla_bar[s], 1);
+      mbar_init(&fulla_bar[s], 1);  // CL == 2: the leader's producer expects the bytes of both CTAs
       mbar_init(&emptya_bar[s], 1);
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(&fullb_bar[s], 1);
-      mbar_init(&emptyb_bar[s], CL);  // freed when every CTA the stage's B half was multicast to has consumed it
+      mbar_init(&emptyb_bar[s], 1);
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], tma_store ? 8 : 4);
-    mbar_init(&tempty_bar[1], tma_store ? 8 : 4);
+    mbar_init(&tempty_bar[0], CL * (tma_store ? 8 : 4));
+    mbar_init(&tempty_bar[1], CL * (tma_store ? 8 : 4));
     fence_barrier_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (CL == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();  // peer barriers are initialised before any multicast lands in them
+  if (CL == 2) cluster_sync_all();  // peer barriers initialised / tensor memory allocated in both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -216,6 +226,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const uint32_t work0 = (CL == 2) ? (blockIdx.x >> 1) : blockIdx.x;
   const uint32_t work_stride = (CL == 2) ? (gridDim.x >> 1) : gridDim.x;
   const uint32_t num_work = (CL == 2) ? p.num_pairs : p.num_tiles;
+  // CL == 2: the leader's barriers as seen through the cluster window (identity mapping for the leader itself)
+  const uint32_t fulla_leader = (CL == 2) ? mapa_shared(smem_u32(fulla_bar), 0) : 0u;
+  const uint32_t fullb_leader = (CL == 2) ? mapa_shared(smem_u32(fullb_bar), 0) : 0u;
+  const uint32_t tempty_leader = (CL == 2) ? mapa_shared(smem_u32(tempty_bar), 0) : 0u;
 
   if (warp_idx == 0) {
     // =============================== TMA producer ===============================
@@ -223,7 +237,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (uint32_t w = work0; w < num_work; w += work_stride) {
-        const uint32_t n_tile = w % p.n_tiles;
         uint32_t idx = (w / p.n_tiles) * CL + cta_rank;  // M-tile (may be a ghost tile past the end: all OOB)
         const int c1 = (idx % p.tiles[1]) * p.box[1];
         idx /= p.tiles[1];
@@ -237,9 +250,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     o3 = p.tap_off[tap][3], o4 = p.tap_off[tap][4];
           for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
             mbar_wait(&emptya_bar[stage], phase ^ 1);
-            mbar_expect_tx(&fulla_bar[stage], A_STAGE_BYTES);
-            tma_load_5d(&p.map_a, &fulla_bar[stage], smem_a + stage * A_STAGE_BYTES,
-                        kc * BLOCK_K + o0, c1 + o1, c2 + o2, c3 + o3, c4 + o4);
+            if (CL == 2) {
+              // the leader expects the activation bytes of both CTAs; each CTA's box lands in its own shared memory
+              if (cta_rank == 0) mbar_expect_tx(&fulla_bar[stage], 2 * A_STAGE_BYTES);
+              tma_load_5d_2sm(&p.map_a, fulla_leader + 8 * stage, smem_a + stage * A_STAGE_BYTES,
+                              kc * BLOCK_K + o0, c1 + o1, c2 + o2, c3 + o3, c4 + o4);
+            } else {
+              mbar_expect_tx(&fulla_bar[stage], A_STAGE_BYTES);
+              tma_load_5d(&p.map_a, &fulla_bar[stage], smem_a + stage * A_STAGE_BYTES,
+                          kc * BLOCK_K + o0, c1 + o1, c2 + o2, c3 + o3, c4 + o4);
+            }
             if (++stage == SA) {
               stage = 0;
               phase ^= 1;
@@ -258,16 +278,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         for (int tap = 0; tap < p.num_taps; ++tap) {
           for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
             mbar_wait(&emptyb_bar[stage], phase ^ 1);
-            mbar_expect_tx(&fullb_bar[stage], Cfg::B_STAGE_BYTES);
             const int kcoord = tap * p.k_per_tap + kc * BLOCK_K;
-            uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+            uint8_t* sb = smem_b + stage * B_STAGE;
             if (CL == 2) {
-              // this CTA's half of the weight tile, delivered to both CTAs (GEGLU: rank 0 = value rows, 1 = gate rows)
+              // this CTA's half of the weight tile (GEGLU: rank 0 = value rows, rank 1 = gate rows)
               const int brow = GEGLU ? (cta_rank == 0 ? n_tile * (BLOCK_N / 2) : p.N / 2 + n_tile * (BLOCK_N / 2))
                                      : (n_tile * BLOCK_N + cta_rank * (BLOCK_N / 2));
-              tma_load_2d_mc(&p.map_b, &fullb_bar[stage], sb + cta_rank * (Cfg::B_STAGE_BYTES / 2), kcoord, brow,
-                             (uint16_t)3);
-            } else if (GEGLU) {
+              if (cta_rank == 0) mbar_expect_tx(&fullb_bar[stage], 2 * B_STAGE);
+              tma_load_2d_2sm(&p.map_b, fullb_leader + 8 * stage, sb, kcoord, brow);
+              if (++stage == SB) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
+            mbar_expect_tx(&fullb_bar[stage], Cfg::B_STAGE_BYTES);
+            if (GEGLU) {
               tma_load_2d(&p.map_b, &fullb_bar[stage], sb, kcoord, n_tile * (BLOCK_N / 2));
               tma_load_2d(&p.map_b, &fullb_bar[stage], sb + Cfg::B_STAGE_BYTES / 2, kcoord,
                           p.N / 2 + n_tile * (BLOCK_N / 2));
@@ -284,14 +310,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp_idx == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(0 /*f16*/, BLOCK_M, BLOCK_N);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(0 /*f16*/, BLOCK_M * CL, BLOCK_N);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       uint32_t it = 0;
       for (uint32_t w = work0; w < num_work; w += work_stride, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (CL == 2) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+        else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -299,16 +326,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           mbar_wait(&fullb_bar[sb], phb);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + sa * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + sb * Cfg::B_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + sb * B_STAGE));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements = 32 bytes along K inside the 128B swizzle row: +2 (>>4)
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (CL == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&emptya_bar[sa]);
-          if (CL == 2) umma_commit_mc(&emptyb_bar[sb], (uint16_t)3);
-          else umma_commit(&emptyb_bar[sb]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (CL == 2) {
+            umma_commit_2sm(&emptya_bar[sa], (uint16_t)3);
+            umma_commit_2sm(&emptyb_bar[sb], (uint16_t)3);
+            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc], (uint16_t)3);
+          } else {
+            umma_commit(&emptya_bar[sa]);
+            umma_commit(&emptyb_bar[sb]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          }
           if (++sa == SA) {
             sa = 0;
             pha ^= 1;
@@ -449,7 +482,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+              if (CL == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+              else mbar_arrive(&tempty_bar[acc]);
+            }
             // publish the staged tile to the async proxy and store it with TMA (clips OOB rows)
             fence_proxy_async();
             epi_bar_sync();
@@ -562,7 +598,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+              if (CL == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+              else mbar_arrive(&tempty_bar[acc]);
+            }
         }
       }
       if (TMA_EPI && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -572,10 +611,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   // teardown
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
+  if (CL == 2) cluster_sync_all();  // the leader may still read / signal this CTA's shared and tensor memory
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CL == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -680,7 +720,7 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   else if (d.N > 16) block_n = 32;
   else block_n = 16;
 
-  // two-CTA clusters (weight-tile multicast) when there are enough M-tiles to keep every SM busy
+  // CTA pairs (cta_group::2) when there are enough M-tiles to keep every SM busy
   uint64_t m_tiles_pre = 1;
   for (int i = 1; i < 5; ++i) m_tiles_pre *= d.tiles[i];
   static const bool cluster_enabled = !(getenv("UAV_IGEMM_CLUSTER") && getenv("UAV_IGEMM_CLUSTER")[0] == '0');
@@ -753,11 +793,11 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
     // ring split inside the fixed RING_BYTES region.  Convolutions re-read their activation tiles from L2
     // (9 taps) -> balanced rings.  Single-tap GEMMs stream activations from HBM (high latency) against L2-resident
     // weights -> deep A ring, shallow B ring.
-    const int b_stage = block_n * BLOCK_K * 2;
+    const int b_stage = block_n * BLOCK_K * 2 / (use_cluster ? 2 : 1);  // CTA pairs hold half a weight tile each
     const int staging = out_tile_n >= 64 ? (out_tile_n / 64) * SLAB_BYTES : 0;
     const int ring = ((232448 - 1024 - staging - 2048) / 1024) * 1024;  // == IgemmCfg::RING_BYTES
     int sb = ring / (A_STAGE_BYTES + b_stage);  // balanced depth
-    if (sb > 8) sb = 8;
+    if (sb > 10) sb = 10;
     int sa = sb;
     // measured on B200: no gain (the weight ring becomes the limiter) -> opt-in only
     static const bool deep_a = getenv("UAV_IGEMM_DEEP_A") && getenv("UAV_IGEMM_DEEP_A")[0] == '1';
@@ -887,6 +927,8 @@ uav_status_t uav_conv2d(const void* x, int64_t NB, int64_t H, int64_t W, int64_t
   UAV_REQUIRE(stride == 1 || stride == 2, "uav_conv2d: stride must be 1 or 2");
   UAV_REQUIRE(pad_mode == 0 || (pad_mode == 1 && stride == 2 && ksize == 3),
               "uav_conv2d: pad_mode 1 needs a stride-2 3x3 conv");
+  // a 1x1 stride-1 convolution is a plain GEMM over the NB*H*W pixels (always-full 128-row tiles)
+  if (ksize == 1 && stride == 1) return uav_linear(x, NB * H * W, Cin, ld_in, w, Cout, out, epi, stream);
   IgemmDesc d;
   memset(&d, 0, sizeof(d));
   d.a = x;
