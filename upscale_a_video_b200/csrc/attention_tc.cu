@@ -4,19 +4,27 @@
 //     320x576 -> 70 TFLOP per frame, 71 % of VAE-decode FLOPs);
 //   * UNet spatial self-attention: 8 heads, d = 128, N = 2880.
 //
-// One CTA = 128 query rows x DVT output columns.  TMEM cannot hold S (128 x 64 fp32, double
-// buffered = 128 columns) plus a 128 x 512 fp32 output accumulator (512 columns), so for d = 512
-// the output is split in two DVT = 256 halves handled by different CTAs (QK^T is recomputed:
-// 1.5x the minimal MMA work; K tiles are shared through L2).
+// One CTA = 128 query rows x DVT output columns, kv tiles of 128 rows.  Tensor memory (512 columns):
+// S double buffered (2 x 128 fp32 columns) + the O accumulator (DVT <= 256 columns); P is written back as packed fp16
+// INTO the S buffer it was computed from and consumed from there as the A operand of the P V MMAs (tcgen05.mma with
+// A in tensor memory), so P costs neither shared memory nor shared-memory bandwidth.  For d = 512 the output does not
+// fit (2 x 128 + 512 columns), so two CTAs each own a 256-wide half of O (QK^T is recomputed: 1.5x the minimal MMA
+// work; K tiles are shared through L2).
 //
-// Warp roles: warp 0 TMA producer (Q once; then a ring of 8 KB [64 x 64] K / V chunk tiles in
-// MMA consumption order), warp 1 single-thread MMA issuer (S_j = Q K_j^T with both operands
-// K-major; O += P_j V_j with P K-major from smem and V MN-major exactly as TMA wrote it),
-// warp 2 TMEM allocator, warps 4-7 softmax: one thread per query row (no shuffles), tcgen05.ld
-// of the score row, exp2 with a lazily updated row maximum (O and l are rescaled only when the
-// maximum grows by more than 2^8, so the TMEM round trip for the correction is rare), P written
-// as fp16 into a 128B-swizzled smem tile.  QK^T of tile j+1 is issued before P_j V_j so the
-// tensor pipe works while the softmax of tile j runs.
+// Shared memory: Q (128 x DQK fp16, up to 128 KB) + a ring of 16 KB slots.  A kv tile streams QSLABS K slots
+// ([128 kv][64 d], K-major) followed by DVT/64 V slots ([128 kv][64 dv], exactly as TMA writes them = MN-major B
+// operand); the ring length is chosen so that the V slots of a tile are always contiguous.
+//
+// Why this shape (measured on the first version: 64-row kv tiles, P through shared memory, 64 KB ring): M=128 x N=64
+// MMAs read 4 KB of A + 2 KB of B from shared memory per 32 tensor-pipe cycles = 192 B/clk against the 128 B/clk the
+// SM can deliver, and the ring held less than one kv tile (96 KB) -> 50 % tensor-pipe utilisation.  N=128 score MMAs
+// halve the A re-reads, P from tensor memory removes them for P V, and the freed 32 KB deepen the ring.
+//
+// Warp roles: warp 0 TMA producer, warp 1 single-thread MMA issuer, warp 2 TMEM allocator, warps 4-7 softmax: one
+// thread per query row (no shuffles), two passes over the score row in tensor memory (row max, then exp2 / pack /
+// tcgen05.st), lazily updated row maximum (O and l are rescaled only when the maximum grows by more than 2^8, so the
+// TMEM round trip for the correction is rare).  QK^T of tile j+1 is issued before P_j V_j so the tensor pipe works
+// while the softmax of tile j runs; all buffer reuse hazards are covered by the in-order tensor pipe.
 #include "uav_common.cuh"
 
 #include <atomic>
@@ -25,11 +33,9 @@
 namespace uav {
 extern std::atomic<uint64_t> g_launches;
 
-constexpr int TC_BM = 128;          // query rows per CTA
-constexpr int TC_BN = 64;           // kv rows per tile
-constexpr int TC_CHUNK_BYTES = 8192;    // [64 rows][64 fp16]
-constexpr int TC_QSLAB_BYTES = 16384;   // [128 rows][64 fp16]
-constexpr int TC_PBUF_BYTES = 16384;    // [128 rows][64 fp16]
+constexpr int TC_BM = 128;            // query rows per CTA
+constexpr int TC_BN = 128;            // kv rows per tile
+constexpr int TC_SLOT_BYTES = 16384;  // [128 rows][64 fp16]
 constexpr int TC_THREADS = 256;
 constexpr float TC_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -44,12 +50,19 @@ struct alignas(64) FaTcParams {
 template <int DQK, int DVT>
 struct FaTcCfg {
   static constexpr int QSLABS = DQK / 64;
-  static constexpr int VCHUNKS = DVT / 64;
-  static constexpr int Q_BYTES = QSLABS * TC_QSLAB_BYTES;
-  static constexpr int RING_RAW = (232448 - 1024 - 1024 - Q_BYTES - 2 * TC_PBUF_BYTES) / TC_CHUNK_BYTES;
-  static constexpr int STAGES = RING_RAW > 12 ? 12 : RING_RAW;
-  static constexpr int SMEM_BYTES = Q_BYTES + 2 * TC_PBUF_BYTES + STAGES * TC_CHUNK_BYTES + 1024 + 1024;
-  static constexpr int TMEM_COLS = (128 + DVT) <= 256 ? 256 : 512;
+  static constexpr int VBLKS = DVT / 64;
+  static constexpr int Q_BYTES = QSLABS * TC_SLOT_BYTES;
+  static constexpr int RING_RAW = (232448 - 1024 - 1024 - Q_BYTES) / TC_SLOT_BYTES;
+  // the V slots of a tile must never wrap around the ring: with QSLABS + VBLKS slots per tile this holds when the ring
+  // length divides the per-tile slot count or is a multiple of it (the V group then always starts at the same offsets)
+  static constexpr int PER_TILE = QSLABS + VBLKS;
+  static constexpr int STAGES = (RING_RAW >= PER_TILE) ? (RING_RAW / PER_TILE) * PER_TILE
+                                                       : (PER_TILE % 6 == 0 && RING_RAW >= 6 ? 6 : 4);
+  static_assert(STAGES <= RING_RAW, "ring does not fit");
+  static_assert((STAGES % PER_TILE == 0) || (PER_TILE % STAGES == 0 && (QSLABS % STAGES) + VBLKS <= STAGES),
+                "V slots of a tile would wrap around the ring");
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * TC_SLOT_BYTES + 1024 + 1024;
+  static constexpr int TMEM_COLS = 512;  // S0 | S1 | O
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -65,11 +78,33 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+        "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A = 128 rows (lanes) x 16 fp16 packed in 8 consecutive 32-bit columns
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
-// MN-major operand tile as written by a TMA box {64 contiguous elements, 64 rows}, SWIZZLE_128B:
+// MN-major operand tile as written by a TMA box {64 contiguous elements, 128 rows}, SWIZZLE_128B:
 // row = one K index (128 bytes = 64 MN elements), 8-row swizzle atoms of 1024 bytes (SBO).
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -87,22 +122,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   using Cfg = FaTcCfg<DQK, DVT>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int QSLABS = Cfg::QSLABS;
-  constexpr int VCHUNKS = Cfg::VCHUNKS;
+  constexpr int VBLKS = Cfg::VBLKS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sq = smem;
-  uint8_t* sp = sq + Cfg::Q_BYTES;             // 2 P buffers
-  uint8_t* ring = sp + 2 * TC_PBUF_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + STAGES * TC_CHUNK_BYTES);
+  uint8_t* ring = sq + Cfg::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + STAGES * TC_SLOT_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* q_bar = bars + 2 * STAGES;       // [1]
-  uint64_t* s_full = q_bar + 1;              // [2]
-  uint64_t* s_free = s_full + 2;             // [2]
-  uint64_t* p_full = s_free + 2;             // [2]
-  uint64_t* p_free = p_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
+  uint64_t* s_full = q_bar + 1;              // [2]  QK^T of a tile landed in S[buf]
+  uint64_t* p_full = s_full + 2;             // [2]  softmax wrote P into S[buf]
+  uint64_t* pv_done = p_full + 2;            // [2]  P V of a tile landed in O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TC_BM;
@@ -125,9 +158,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(q_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
       mbar_init(&p_full[i], 4);
-      mbar_init(&p_free[i], 1);
+      mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
   }
@@ -136,31 +168,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + 2 * TC_BN;
 
   if (warp_idx == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       mbar_expect_tx(q_bar, Cfg::Q_BYTES);
       for (int c = 0; c < QSLABS; ++c)
-        tma_load_3d(&p.map_q, q_bar, sq + c * TC_QSLAB_BYTES, h * DQK + c * 64, q0, b);
+        tma_load_3d(&p.map_q, q_bar, sq + c * TC_SLOT_BYTES, h * DQK + c * 64, q0, b);
       int stage = 0;
       uint32_t phase = 0;
-      auto load_chunk = [&](const CUtensorMap* map, int col, int row) {
+      auto load_slot = [&](const CUtensorMap* map, int col, int row) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], TC_CHUNK_BYTES);
-        tma_load_3d(map, &full_bar[stage], ring + stage * TC_CHUNK_BYTES, col, row, bkv);
+        mbar_expect_tx(&full_bar[stage], TC_SLOT_BYTES);
+        tma_load_3d(map, &full_bar[stage], ring + stage * TC_SLOT_BYTES, col, row, bkv);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       };
       auto load_k = [&](int j) {
-        for (int c = 0; c < QSLABS; ++c) load_chunk(&p.map_k, h * DQK + c * 64, j * TC_BN);
+        for (int c = 0; c < QSLABS; ++c) load_slot(&p.map_k, h * DQK + c * 64, j * TC_BN);
       };
       auto load_v = [&](int j) {
-        for (int c = 0; c < VCHUNKS; ++c)
-          load_chunk(&p.map_v, h * (DVT * (int)gridDim.y) + dv_off + c * 64, j * TC_BN);
+        for (int c = 0; c < VBLKS; ++c)
+          load_slot(&p.map_v, h * (DVT * (int)gridDim.y) + dv_off + c * 64, j * TC_BN);
       };
       // same order as the MMA warp consumes: K0, {K(j+1), V(j)}...
       load_k(0);
@@ -176,18 +208,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       constexpr uint32_t idesc_pv = umma_idesc(0, TC_BM, 64) | (1u << 16);  // B is MN-major
       int stage = 0;
       uint32_t phase = 0;
+      // S[buf] = Q K_j^T.  S[buf] last held P_{j-2}, whose P V MMAs precede this in the (in-order) tensor pipe.
       auto issue_qk = [&](int j) {
         const uint32_t sb = j & 1;
-        mbar_wait(&s_free[sb], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
         for (int c = 0; c < QSLABS; ++c) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sq + c * TC_QSLAB_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + stage * TC_CHUNK_BYTES));
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sq + c * TC_SLOT_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + stage * TC_SLOT_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + sb * 64, adesc + 2 * k, bdesc + 2 * k, idesc_qk, (c | k) != 0);
+            umma_f16(tmem_base + sb * TC_BN, adesc + 2 * k, bdesc + 2 * k, idesc_qk, (c | k) != 0);
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
@@ -201,24 +232,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       issue_qk(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_qk(j + 1);
-        const uint32_t pb = j & 1;
-        mbar_wait(&p_full[pb], (j >> 1) & 1);
+        const uint32_t sb = j & 1;
+        mbar_wait(&p_full[sb], (j >> 1) & 1);
         tc_fence_after();
-        for (int c = 0; c < VCHUNKS; ++c) {
+        const uint32_t tmem_p = tmem_base + sb * TC_BN;  // packed fp16 P: 64 columns
+        for (int c = 0; c < VBLKS; ++c) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sp + pb * TC_PBUF_BYTES));
-          const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(ring + stage * TC_CHUNK_BYTES));
+          const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(ring + stage * TC_SLOT_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 16 kv rows per step: A +32 B (K-major), B +16 rows * 128 B
-            umma_f16(tmem_o + c * 64, adesc + 2 * k, bdesc + 128 * k, idesc_pv, (j | k) != 0);
+          for (int k = 0; k < TC_BN / 16; ++k)  // 16 kv rows per step: A +8 columns, B +16 rows * 128 B
+            umma_f16_ts(tmem_o + c * 64, tmem_p + 8 * k, bdesc + 128 * k, idesc_pv, (j | k) != 0);
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&p_free[pb]);
+        umma_commit(&pv_done[sb]);
       }
     }
   } else if (warp_idx >= 4) {
@@ -229,26 +260,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t sb = j & 1;
+      const uint32_t tmem_s = tmem_base + lane_addr + sb * TC_BN;
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32(tmem_base + lane_addr + sb * 64, s0);
-      tmem_ld_32x32(tmem_base + lane_addr + sb * 64 + 32, s1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[sb]);
-
       const int kbase = j * TC_BN;
-      float x[64];
+      const int valid = p.nk - kbase;  // columns >= valid are padding
+      // ---- pass 1: row maximum ----
       float mx = -INFINITY;
+#pragma unroll 1
+      for (int blk = 0; blk < TC_BN / 32; ++blk) {
+        uint32_t s[32];
+        tmem_ld_32x32(tmem_s + blk * 32, s);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float v = __uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]) * p.scale_log2;
-        if (kbase + c >= p.nk) v = -INFINITY;
-        x[c] = v;
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < 32; ++c)
+          if (blk * 32 + c < valid) mx = fmaxf(mx, __uint_as_float(s[c]));
       }
+      mx *= p.scale_log2;  // scale > 0
       float alpha = 1.f;
       bool need = false;
       if (j == 0) {
@@ -260,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       if (__any_sync(0xffffffffu, need)) {
         // all PVs up to tile j-1 must have landed in O before it is rescaled
-        mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < DVT / 32; ++c) {
@@ -274,31 +302,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tmem_st_wait();
         l_run *= alpha;
       }
+      // ---- pass 2: P = exp2(S * scale - m), packed fp16 written over the first half of the S buffer ----
       float rs = 0.f;
-      uint32_t pk[32];
+#pragma unroll 1
+      for (int blk = 0; blk < TC_BN / 32; ++blk) {
+        uint32_t s[32];
+        tmem_ld_32x32(tmem_s + blk * 32, s);
+        tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float p0 = exp2f(x[2 * c] - m_run), p1 = exp2f(x[2 * c + 1] - m_run);
-        rs += p0 + p1;
-        __half2 hh = __floats2half2_rn(p0, p1);
-        pk[c] = *reinterpret_cast<uint32_t*>(&hh);
+        for (int c = 0; c < 16; ++c) {
+          float p0 = exp2f(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -m_run));
+          float p1 = exp2f(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -m_run));
+          if (blk * 32 + 2 * c >= valid) p0 = 0.f;
+          if (blk * 32 + 2 * c + 1 >= valid) p1 = 0.f;
+          rs += p0 + p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          pk[c] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        tmem_st_32x16(tmem_s + blk * 16, pk);  // columns [16 blk, +16) <= columns already consumed
       }
       l_run += rs;
-      // P buffer sb is free once the PV of tile j-2 completed
-      mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
-      uint8_t* prow = sp + sb * TC_PBUF_BYTES + row * 128;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 v = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = v;
-      }
-      fence_proxy_async();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
     }
     // ---- epilogue: O / l -> global ----
-    mbar_wait(&p_free[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+    mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const bool row_ok = q0 + row < p.nq;

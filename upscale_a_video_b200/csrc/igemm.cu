@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     igemm_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
   static_assert(!TMA_EPI || Cfg::OUT_TILE_N >= 64, "TMA-store epilogue needs >= 64-column output tiles");
-  constexpr int STAGES = Cfg::STAGES;
   constexpr int OUT_TILE_N = Cfg::OUT_TILE_N;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (SWIZZLE_128B atoms) in the shared address space
