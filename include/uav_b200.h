@@ -218,6 +218,33 @@ uav_status_t uav_propagate_step(const void* feat_prop, const void* feat_cur, con
                                 float fuse_scale, float alpha1, float alpha2, int half_grid_sample,
                                 int dtype, uav_stream_t stream);
 
+/* ---- after the decode: colour fix + output packing ---------------------------------
+ * All tensors are the reference's planar fp32 "t c h w" frames (planes = t * c). */
+
+/* F.interpolate(vframes, scale_factor=scale, mode='bicubic') of the low-resolution frames before the colour fix
+ * (inference_upscale_a_video.py:327): align_corners=False, A=-0.75, border-clamped taps. out: [planes][h*scale][w*scale] */
+uav_status_t uav_bicubic_upsample(const float* in, int64_t planes, int64_t h, int64_t w, int scale, float* out,
+                                  uav_stream_t stream);
+/* calc_mean_std (color_correction.py:45-58): per plane mean and sqrt(unbiased var + eps) over hw elements.
+ * Deterministic (no atomics). workspace: uav_plane_stats_workspace_bytes(planes) bytes, 16-byte aligned. */
+size_t uav_plane_stats_workspace_bytes(int64_t planes);
+uav_status_t uav_plane_stats(const float* x, int64_t planes, int64_t hw, float eps, void* workspace, float* mean,
+                             float* stdv, uav_stream_t stream);
+/* adaptive_instance_normalization (color_correction.py:60-73):
+ * out = (content - c_mean[plane]) / c_std[plane] * s_std[plane] + s_mean[plane], one rounding per reference op */
+uav_status_t uav_adain_apply(const float* content, int64_t planes, int64_t hw, const float* c_mean, const float* c_std,
+                             const float* s_mean, const float* s_std, float* out, uav_stream_t stream);
+/* one level of wavelet_decomposition (color_correction.py:75-103): low = wavelet_blur(image, radius) (depthwise
+ * [1 2 1; 2 4 2; 1 2 1]/16, dilation = radius, replicate padding); if high != NULL: high = image - low
+ * (high_first != 0) or high += image - low; if add != NULL the value written to `low` is add + low (the final
+ * content_high_freq + style_low_freq of wavelet_reconstruction, :105-118). low may be NULL. Outputs must not alias image. */
+uav_status_t uav_wavelet_level(const float* image, int64_t planes, int64_t H, int64_t W, int radius, float* low,
+                               float* high, int high_first, const float* add, uav_stream_t stream);
+/* (frames / 2 + 0.5).clamp(0, 1) * 255 -> "t h w c" -> uint8 by truncation (inference_upscale_a_video.py:354-356).
+ * frames: [T][C][H][W] fp32, out: [T][H][W][C] uint8, C <= 4. Bit-exact. */
+uav_status_t uav_pack_video_uint8(const float* frames, int64_t T, int64_t C, int64_t H, int64_t W, uint8_t* out,
+                                  uav_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,32 @@ def test_pipeline(unet_sd, case):
                                    return_latents=True)
     torch.testing.assert_close(lat, c["latents_out"], rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(out, c["out"], rtol=1e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# colour fix + packing: oracle/color_oracle.py vs the reference's own functions
+# ------------------------------------------------------------------------------------------------
+def test_color_oracle_against_reference_fixtures():
+    from oracle import color_oracle as co
+
+    cases = _load("color.pt")
+    assert set(cases) == {"t2_16x24", "t1_13x19"}
+    for name, c in cases.items():
+        lr, hr = c["lr"], c["hr"]
+        up = co.bicubic_upsample(lr, 4)
+        assert (up - c["bicubic"]).abs().max().item() < 2e-6, name
+        mean, std = co.calc_mean_std(hr)
+        assert (mean - c["mean"]).abs().max().item() < 1e-6 and (std - c["std"]).abs().max().item() < 1e-6, name
+        # tolerance in the test: fp32 reductions / 9-tap sums in a different association order
+        assert (co.adaptive_instance_normalization(hr, c["bicubic"]) - c["adain"]).abs().max().item() < 5e-6, name
+        assert (co.wavelet_reconstruction(hr, c["bicubic"]) - c["wavelet"]).abs().max().item() < 2e-6, name
+        if "high" in c:
+            high, low = co.wavelet_decomposition(hr)
+            assert (high - c["high"]).abs().max().item() < 2e-6 and (low - c["low"]).abs().max().item() < 1e-6, name
+            assert (co.wavelet_blur(hr, 4) - c["blur4"]).abs().max().item() < 1e-6, name
+        # integer work: bit-exact
+        assert torch.equal(co.pack_video_uint8(hr), c["pack_hr"]), name
+        assert torch.equal(co.pack_video_uint8(c["adain"]), c["pack_adain"]), name
+        # the CLI block end to end (inference_upscale_a_video.py:323-333)
+        out = co.color_fix_frames(hr.permute(1, 0, 2, 3)[None], lr.permute(1, 0, 2, 3)[None], "Wavelet")
+        assert (out - c["wavelet"]).abs().max().item() < 5e-6, name

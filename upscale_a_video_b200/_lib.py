@@ -59,12 +59,18 @@ _PROTOS = {
     "uav_add_noise": [P, P, P, I64, F32, F32, I32, P],
     "uav_propagate_step": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I32, I32, F32, F32, F32,
                            I32, I32, P],
+    "uav_bicubic_upsample": [P, I64, I64, I64, I32, P, P],
+    "uav_plane_stats": [P, I64, I64, F32, P, P, P, P],
+    "uav_adain_apply": [P, I64, I64, P, P, P, P, P, P],
+    "uav_wavelet_level": [P, I64, I64, I64, I32, P, P, I32, P, P],
+    "uav_pack_video_uint8": [P, I64, I64, I64, I64, P, P],
 }
 _SPECIAL = {
     "uav_version": (C.c_char_p, []),
     "uav_last_error_string": (C.c_char_p, []),
     "uav_launch_count": (C.c_uint64, []),
     "uav_groupnorm_workspace_bytes": (C.c_size_t, [I64, I32]),
+    "uav_plane_stats_workspace_bytes": (C.c_size_t, [I64]),
 }
 
 

@@ -501,3 +501,66 @@ def propagate_step(feat_prop, feat_cur, flow_prop, flow_check, out, *, nearest: 
                                       1 if nearest else 0, 1 if fuse else 0, fuse_scale, alpha1, alpha2,
                                       1 if half_grid_sample else 0, dt, _stream()), "uav_propagate_step")
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# after the decode: colour fix + output packing (csrc/postprocess.cu) — planar fp32 "t c h w" frames
+# ---------------------------------------------------------------------------------------
+def _f32_planes(x: torch.Tensor) -> torch.Tensor:
+    assert x.is_cuda and x.dim() == 4, "expected a CUDA (t, c, h, w) tensor"
+    return x.float().contiguous()
+
+
+def bicubic_upsample(x: torch.Tensor, scale: int = 4) -> torch.Tensor:
+    """F.interpolate(x, scale_factor=scale, mode='bicubic') for a (t, c, h, w) fp32 tensor"""
+    x = _f32_planes(x)
+    t, c, h, w = x.shape
+    out = torch.empty(t, c, h * scale, w * scale, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_bicubic_upsample(x.data_ptr(), t * c, h, w, scale, out.data_ptr(), _stream()), "uav_bicubic_upsample")
+    return out
+
+
+def plane_stats(x: torch.Tensor, eps: float = 1e-5):
+    """calc_mean_std: (mean, sqrt(unbiased var + eps)) per (t, c) plane, each shaped (t, c, 1, 1)"""
+    x = _f32_planes(x)
+    t, c, h, w = x.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.uav_plane_stats_workspace_bytes(t * c), dtype=torch.uint8, device=x.device)
+    mean = torch.empty(t, c, 1, 1, dtype=torch.float32, device=x.device)
+    std = torch.empty_like(mean)
+    _lib.check(lib.uav_plane_stats(x.data_ptr(), t * c, h * w, eps, ws.data_ptr(), mean.data_ptr(), std.data_ptr(),
+                                   _stream()), "uav_plane_stats")
+    return mean, std
+
+
+def adain_apply(content: torch.Tensor, c_mean, c_std, s_mean, s_std) -> torch.Tensor:
+    content = _f32_planes(content)
+    t, c, h, w = content.shape
+    out = torch.empty_like(content)
+    lib = _lib.load()
+    _lib.check(lib.uav_adain_apply(content.data_ptr(), t * c, h * w, c_mean.data_ptr(), c_std.data_ptr(),
+                                   s_mean.data_ptr(), s_std.data_ptr(), out.data_ptr(), _stream()), "uav_adain_apply")
+    return out
+
+
+def wavelet_level(image: torch.Tensor, radius: int, *, low: Optional[torch.Tensor] = None,
+                  high: Optional[torch.Tensor] = None, high_first: bool = False, add: Optional[torch.Tensor] = None):
+    """one a-trous level: low <- blur(image) (+ add), high (+)= image - blur(image)"""
+    t, c, h, w = image.shape
+    for x in (image, low, high, add):
+        assert x is None or (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape == image.shape)
+    lib = _lib.load()
+    _lib.check(lib.uav_wavelet_level(image.data_ptr(), t * c, h, w, radius, low.data_ptr() if low is not None else None,
+                                     high.data_ptr() if high is not None else None, 1 if high_first else 0,
+                                     add.data_ptr() if add is not None else None, _stream()), "uav_wavelet_level")
+
+
+def pack_video_uint8(frames: torch.Tensor) -> torch.Tensor:
+    """(t, c, h, w) in [-1, 1] -> (t, h, w, c) uint8, as the reference packs frames for imageio"""
+    frames = _f32_planes(frames)
+    t, c, h, w = frames.shape
+    out = torch.empty(t, h, w, c, dtype=torch.uint8, device=frames.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_pack_video_uint8(frames.data_ptr(), t, c, h, w, out.data_ptr(), _stream()), "uav_pack_video_uint8")
+    return out
