@@ -47,9 +47,8 @@ cases["conv_t3 512 @160x288"] = (lambda: ops.conv_temporal(xt, wt, b), 2.0 * xt.
 am = rnd(46080, 1024); wm = rnd(1024, 1024, scale=0.02); bm = torch.zeros(1024, device=dev)
 cases["linear 1024 M46080"] = (lambda: ops.linear(am, wm, bm), 2.0 * am.numel() * 1024)
 
-variants = [("1cta", {"UAV_IGEMM_CLUSTER": "0", "UAV_IGEMM_DBG": "0"}),
-            ("2cta", {"UAV_IGEMM_CLUSTER": "1", "UAV_IGEMM_DBG": "0"}),
-            ("2cta-1commit", {"UAV_IGEMM_CLUSTER": "1", "UAV_IGEMM_DBG": "1"})]
+# the library reads UAV_IGEMM_CLUSTER once per process: run this script twice (UAV_IGEMM_CLUSTER=0 / 1) to compare
+variants = [("cluster=%s" % os.environ.get("UAV_IGEMM_CLUSTER", "1"), {})]
 times = {(c, v): [] for c in cases for v, _ in variants}
 for rnd_i in range(6):
     for c, (fn, fl) in cases.items():

@@ -276,22 +276,37 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t ab_fmt, uint32_t M, u
 }
 
 // ---- misc math ----
-// fast division (<= 2 ulp): keeps the IEEE-division slow path (and its code size) out of every epilogue
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// exact-GELU x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + 9 FP32 ops instead
-// of the ~25-instruction two-branch erff(); the negative side uses erfc directly (no 1 + erf cancellation).  Absolute
-// error of the result <= 4.3e-7 (same as the fp32 0.5 x (1 + erff(x / sqrt 2)) formula against float64).
+// MUFU.EX2 / MUFU.RCP with flush-to-zero: the non-ftz forms (__expf, __fdividef) wrap every MUFU in denormal
+// range fix-ups (FSETP + predicated FMULs: ~8 extra instructions per GELU), which matters in the GEMM epilogues that
+// are issue-bound.  <= 2 ulp; results that would be denormal flush to zero (|x| > 87 for SiLU, > 13 for GELU tails).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// x * sigmoid(x): x -> -inf gives x * rcp(inf) = -0, x -> +inf gives x * rcp(1) = x
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+// exact-GELU x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + 12 FP32 ops instead
+// of the ~25-instruction two-branch erff(); the negative side uses erfc directly (no 1 + erf cancellation).  With
+// z = x / sqrt(2): t = 1 / (1 + p z), erfc(|z|) = t * poly(t) * exp(-z^2); Phi = 1 - erfc/2 (x >= 0) or erfc/2 (x < 0).
+// The 1/2 is folded into the polynomial, p / sqrt(2) and log2(e) / 2 into the constants.  Absolute error of the
+// result <= 4.3e-7 (same as the fp32 0.5 x (1 + erff(x / sqrt 2)) formula against float64).
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-  float q = fmaf(1.061405429f, t, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  const float s = q * t * __expf(-az * az);  // erfc(|z|)
-  const float one_plus_erf = (z >= 0.0f) ? 2.0f - s : s;
-  return 0.5f * x * one_plus_erf;
+  const float ax = fabsf(x);
+  const float t = rcp_ftz(fmaf(0.2316418882663604f, ax, 1.0f));
+  const float e = ex2_ftz(-0.7213475204444817f * x * x);
+  float q = fmaf(0.5307027145f, t, -0.7265760135f);
+  q = fmaf(q, t, 0.7107068705f);
+  q = fmaf(q, t, -0.142248368f);
+  q = fmaf(q, t, 0.127414796f);
+  const float s = q * t * e;  // erfc(|z|) / 2
+  const float phi = (x >= 0.0f) ? 1.0f - s : s;
+  return x * phi;
 }
 
 // 16-byte global access
