@@ -22,3 +22,18 @@ for name, B, heads, d, n in [("vae d512 N=46080", 1, 1, 512, 46080), ("vae d512 
     out = torch.empty(B, n, C, device="cuda", dtype=torch.float16)
     ms = timeit(lambda: ops.attention(qkv[..., :C], qkv[..., C:2*C], qkv[..., 2*C:], heads, out=out))
     print(json.dumps({"impl": tag, "name": name, "ms": ms, "tflops_alg": 4.0 * B * n * n * C / ms / 1e9}))
+
+# temporal attention at the top UNet level (B=2, T=8, 160x288, 8 heads x 64): 8 B/element stream
+import math
+B, Fr, HW, heads, d = 2, 8, 160 * 288, 8, 64
+C = heads * d
+qkv = torch.randn(B, Fr, HW, 3 * C, device="cuda").half()
+q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32))
+ang = torch.arange(Fr).float()[:, None] * freqs[None, :]
+rot = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous().cuda()
+bias = (torch.randn(heads, Fr, Fr) * 0.3).cuda()
+out = torch.empty(B, Fr, HW, C, device="cuda", dtype=torch.float16)
+ms = timeit(lambda: ops.temporal_attention(q, k, v, heads, rot, bias, out=out), iters=10, warmup=3)
+print(json.dumps({"impl": "shfl" if os.environ.get("UAV_TEMPORAL_SHFL") == "1" else "mma", "name": "temporal attn 2x8x46080 h8 d64",
+                  "ms": ms, "GBps": 4 * B * Fr * HW * C * 2 / ms / 1e6}))

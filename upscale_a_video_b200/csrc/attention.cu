@@ -557,6 +557,161 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// temporal attention on mma.sync: one warp per PAIR of heads of one (batch, pixel).
+// The two items' 8 frames are stacked into one 16-row tile, so that
+//   S  = [Q_a; Q_b] K_a^T , [Q_a; Q_b] K_b^T   (two m16n8k16 n-blocks per k-step; the cross terms are discarded)
+//   O  = diag(P_a, P_b) [V_a; V_b]              (ONE k-step: the block-diagonal P is exactly the A fragment
+//                                                {P_a, 0, 0, P_b} built from the S accumulators in registers)
+// ~125 instructions per (pixel, head) instead of ~700 for the shuffle formulation above (which is kept for an odd
+// head count): the kernel becomes a pure 8 B/element stream.  Rotary (first 32 dims, interleaved pairs) is applied to
+// the 16-byte chunks on their way into shared memory; scale and the relative-position bias are applied to the fp32
+// scores.
+// ---------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+    temporal_attn_mma_kernel(const TaParams p) {
+  constexpr int CH = D / 8;             // 16-byte chunks per row
+  constexpr int LD_ITERS = 16 * CH / 32;  // chunks per lane and tensor
+  __shared__ __align__(16) __half smem[4][3][16 * D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hp = p.heads >> 1;
+  const int64_t pw = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  const int64_t total = static_cast<int64_t>(p.B) * p.HW * hp;
+  if (pw >= total) return;  // whole warp
+  const int h0 = static_cast<int>(pw % hp) * 2;
+  const int64_t pix = (pw / hp) % p.HW;
+  const int64_t b = pw / (static_cast<int64_t>(hp) * p.HW);
+  __half* sQ = smem[warp][0];
+  __half* sK = smem[warp][1];
+  __half* sV = smem[warp][2];
+
+  // ---- global -> (rotary) -> swizzled smem tiles: row = item * 8 + frame.  All loads are issued before the first
+  // use so that 3 * LD_ITERS 16-byte requests per lane are in flight ----
+  uint4 v[3][LD_ITERS];
+#pragma unroll
+  for (int tsr = 0; tsr < 3; ++tsr) {
+    const __half* src = tsr == 0 ? p.q : (tsr == 1 ? p.k : p.v);
+    const int64_t ld = tsr == 0 ? p.ldq : (tsr == 1 ? p.ldk : p.ldv);
+#pragma unroll
+    for (int i = 0; i < LD_ITERS; ++i) {
+      const int id = lane + 32 * i;
+      const int row = id / CH, chunk = id % CH;
+      const int item = row >> 3, frame = row & 7;
+      v[tsr][i] = make_uint4(0, 0, 0, 0);
+      if (frame < p.F) {
+        const int64_t tok = (b * p.F + frame) * p.HW + pix;
+        v[tsr][i] = ldg16(src + tok * ld + (h0 + item) * D + chunk * 8);
+      }
+    }
+  }
+#pragma unroll
+  for (int tsr = 0; tsr < 3; ++tsr) {
+    __half* dst = smem[warp][tsr];
+#pragma unroll
+    for (int i = 0; i < LD_ITERS; ++i) {
+      const int id = lane + 32 * i;
+      const int row = id / CH, chunk = id % CH;
+      const int frame = row & 7;
+      if (tsr < 2 && chunk < 4 && frame < p.F) {
+        // rotary pairs 4*chunk .. 4*chunk+3 of this frame: (x0, x1) -> (x0 c - x1 s, x1 c + x0 s)
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.rot + (frame * 16 + chunk * 4) * 2));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.rot + (frame * 16 + chunk * 4) * 2 + 4));
+        const float cs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        __half2* h = reinterpret_cast<__half2*>(&v[tsr][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          const float c = cs[2 * j], sn = cs[2 * j + 1];
+          h[j] = __floats2half2_rn(f.x * c - f.y * sn, f.y * c + f.x * sn);
+        }
+      }
+      *reinterpret_cast<uint4*>(tile_ptr<D>(dst, row, chunk)) = v[tsr][i];
+    }
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  // ---- S = Q K^T ----
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, achk = lane >> 4;
+    const int brow = (lane & 7) + (lane >> 4) * 8, bchk = (lane >> 3) & 1;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      uint32_t a[4], bfr[4];
+      ldmatrix_x4(a, tile_ptr<D>(sQ, arow, kk * 2 + achk));
+      ldmatrix_x4(bfr, tile_ptr<D>(sK, brow, kk * 2 + bchk));
+      mma16816(s0, a, bfr[0], bfr[1]);  // keys of item a
+      mma16816(s1, a, bfr[2], bfr[3]);  // keys of item b
+    }
+  }
+  // ---- softmax over the <= 8 keys of each item: row g of item a lives in s0[0..1], row g of item b in s1[2..3] ----
+  uint32_t pa, pb;
+  {
+    const int j0 = 2 * t4, j1 = j0 + 1;
+    const bool row_ok = g < p.F;
+    float xa0 = -INFINITY, xa1 = -INFINITY, xb0 = -INFINITY, xb1 = -INFINITY;
+    if (row_ok && j0 < p.F) {
+      xa0 = s0[0] * p.scale + __ldg(p.bias + (h0 * p.F + g) * p.F + j0);
+      xb0 = s1[2] * p.scale + __ldg(p.bias + ((h0 + 1) * p.F + g) * p.F + j0);
+    }
+    if (row_ok && j1 < p.F) {
+      xa1 = s0[1] * p.scale + __ldg(p.bias + (h0 * p.F + g) * p.F + j1);
+      xb1 = s1[3] * p.scale + __ldg(p.bias + ((h0 + 1) * p.F + g) * p.F + j1);
+    }
+    float ma = fmaxf(xa0, xa1), mb = fmaxf(xb0, xb1);
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    if (!row_ok) ma = mb = 0.f;  // padded query rows: all keys masked, keep the arithmetic finite
+    const float ea0 = __expf(xa0 - ma), ea1 = __expf(xa1 - ma), eb0 = __expf(xb0 - mb), eb1 = __expf(xb1 - mb);
+    float da = ea0 + ea1, db = eb0 + eb1;
+    da += __shfl_xor_sync(0xffffffffu, da, 1);
+    db += __shfl_xor_sync(0xffffffffu, db, 1);
+    da += __shfl_xor_sync(0xffffffffu, da, 2);
+    db += __shfl_xor_sync(0xffffffffu, db, 2);
+    const float ia = da > 0.f ? 1.f / da : 0.f, ib = db > 0.f ? 1.f / db : 0.f;
+    __half2 ha = __floats2half2_rn(ea0 * ia, ea1 * ia), hb = __floats2half2_rn(eb0 * ib, eb1 * ib);
+    pa = *reinterpret_cast<uint32_t*>(&ha);
+    pb = *reinterpret_cast<uint32_t*>(&hb);
+  }
+  // ---- O = diag(P_a, P_b) [V_a; V_b] ----
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  {
+    const uint32_t a[4] = {pa, 0u, 0u, pb};
+    const int vrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int nb = 0; nb < D / 16; ++nb) {
+      uint32_t bfr[4];
+      ldmatrix_x4_trans(bfr, tile_ptr<D>(sV, vrow, nb * 2 + (lane >> 4)));
+      mma16816(o[nb * 2], a, bfr[0], bfr[1]);
+      mma16816(o[nb * 2 + 1], a, bfr[2], bfr[3]);
+    }
+  }
+  // ---- O -> smem (Q tile) -> 16-byte stores ----
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < D / 8; ++n) {
+    *reinterpret_cast<__half2*>(tile_ptr<D>(sQ, g, n) + 2 * t4) = __floats2half2_rn(o[n][0], o[n][1]);
+    *reinterpret_cast<__half2*>(tile_ptr<D>(sQ, g + 8, n) + 2 * t4) = __floats2half2_rn(o[n][2], o[n][3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < LD_ITERS; ++i) {
+    const int id = lane + 32 * i;
+    const int row = id / CH, chunk = id % CH;
+    const int item = row >> 3, frame = row & 7;
+    if (frame < p.F) {
+      const int64_t tok = (b * p.F + frame) * p.HW + pix;
+      stg16(p.o + tok * p.ldo + (h0 + item) * D + chunk * 8, *reinterpret_cast<const uint4*>(tile_ptr<D>(sQ, row, chunk)));
+    }
+  }
+}
+
 uav_status_t attention_tc(const void* q, const void* k, const void* v, void* out, int64_t batch,
                           int heads, int head_dim, int64_t nq, int64_t nk, int64_t ldq, int64_t ldk,
                           int64_t ldv, int64_t ldo, int64_t kv_batch_div, float scale,
@@ -660,7 +815,13 @@ uav_status_t uav_temporal_attention(const void* q, const void* k, const void* v,
   p.scale = scale; p.rot = rot_cos_sin; p.bias = rel_bias;
   const int64_t warps = B * HW * heads;
   const unsigned grid = (unsigned)((warps + 7) / 8);
-  if (head_dim == 64) temporal_attn_kernel<64><<<grid, 256, 0, stream>>>(p);
+  static const bool force_shfl = getenv("UAV_TEMPORAL_SHFL") && getenv("UAV_TEMPORAL_SHFL")[0] == '1';
+  if (heads % 2 == 0 && !force_shfl && (head_dim == 64 || head_dim == 128)) {
+    // mma.sync formulation: one warp per pair of heads
+    const unsigned grid2 = (unsigned)((warps / 2 + 3) / 4);
+    if (head_dim == 64) temporal_attn_mma_kernel<64><<<grid2, 128, 0, stream>>>(p);
+    else temporal_attn_mma_kernel<128><<<grid2, 128, 0, stream>>>(p);
+  } else if (head_dim == 64) temporal_attn_kernel<64><<<grid, 256, 0, stream>>>(p);
   else if (head_dim == 128) temporal_attn_kernel<128><<<grid, 256, 0, stream>>>(p);
   else {
     set_last_error("uav_temporal_attention: head_dim %d unsupported (64, 128)", head_dim);
