@@ -37,3 +37,12 @@ out = torch.empty(B, Fr, HW, C, device="cuda", dtype=torch.float16)
 ms = timeit(lambda: ops.temporal_attention(q, k, v, heads, rot, bias, out=out), iters=10, warmup=3)
 print(json.dumps({"impl": "shfl" if os.environ.get("UAV_TEMPORAL_SHFL") == "1" else "mma", "name": "temporal attn 2x8x46080 h8 d64",
                   "ms": ms, "GBps": 4 * B * Fr * HW * C * 2 / ms / 1e6}))
+
+# text cross-attention at the top UNet level: 16 frames x 46080 queries, 77 keys, 8 heads x 64 (4 B/element stream of q, o)
+B, heads, d, nq, nk = 16, 8, 64, 46080, 77
+C = heads * d
+q = torch.randn(B, nq, C, device="cuda").half()
+kv = torch.randn(2, nk, 2 * C, device="cuda").half()
+out = torch.empty(B, nq, C, device="cuda", dtype=torch.float16)
+ms = timeit(lambda: ops.attention(q, kv[..., :C], kv[..., C:], heads, kv_batch_div=8, out=out), iters=10, warmup=3)
+print(json.dumps({"name": "cross attn b16 h8 d64 nq46080 nk77", "ms": ms, "GBps": 2 * B * nq * C * 2 / ms / 1e6}))

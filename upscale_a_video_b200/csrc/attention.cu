@@ -267,8 +267,10 @@ __global__ void __launch_bounds__(FA_THREADS)
   __half* sv = sk + NKP * D;                          // [NKP][D]
   __half* sq = sv + NKP * D;                          // [2][64][D]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.y;
-  const int b = bh / p.heads, h = bh % p.heads;
+  // the head is the FASTEST block index: the CTAs that read the 2*D-byte head slices of the same token rows run side
+  // by side, so each 1 KB token row is fetched from DRAM within one burst instead of once per head pass
+  const int b = blockIdx.y, h = blockIdx.x % p.heads;
+  const int tile_stride = gridDim.x / p.heads;
   const __half* qg = p.q + b * p.bsq + static_cast<int64_t>(h) * D;
   const __half* kg = p.k + (b / p.kv_batch_div) * p.bsk + static_cast<int64_t>(h) * D;
   const __half* vg = p.v + (b / p.kv_batch_div) * p.bsv + static_cast<int64_t>(h) * D;
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(FA_THREADS)
       cp_async16(tile_ptr<D>(sqb, r, c), qg + static_cast<int64_t>(ok ? q0 + r : 0) * p.ldq + c * 8, ok);
     }
   };
-  int tile = blockIdx.x;
+  int tile = blockIdx.x / p.heads;
   if (tile < ntiles) load_q(tile, 0);
   cp_async_commit();
 
@@ -299,9 +301,9 @@ __global__ void __launch_bounds__(FA_THREADS)
   const int arow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
   const int achk = lane >> 4;
   int it = 0;
-  for (; tile < ntiles; tile += gridDim.x, ++it) {
+  for (; tile < ntiles; tile += tile_stride, ++it) {
     const int buf = it & 1;
-    const int next = tile + gridDim.x;
+    const int next = tile + tile_stride;
     if (next < ntiles) load_q(next, buf ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
@@ -326,29 +328,32 @@ __global__ void __launch_bounds__(FA_THREADS)
         mma16816(s[nb * 2 + 1], a, bfr[2], bfr[3]);
       }
     }
+    // row maxima of the raw scores (scale > 0); only 8-column blocks past nk hold padded keys
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nb = 0; nb < NB16 * 2; ++nb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int col = nb * 8 + t4 * 2 + (e & 1);
-        float x = s[nb][e] * p.scale_log2;
-        if (col >= p.nk) x = -INFINITY;
-        s[nb][e] = x;
-        mx[e >> 1] = fmaxf(mx[e >> 1], x);
+        if ((nb + 1) * 8 > p.nk) {  // block-uniform test, false for all but the tail blocks
+          const int col = nb * 8 + t4 * 2 + (e & 1);
+          if (col >= p.nk) s[nb][e] = -INFINITY;
+        }
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nb][e]);
       }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffff, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffff, mx[r], 2));
+      mx[r] *= p.scale_log2;
     }
     float rs[2] = {0.f, 0.f};
     uint32_t pf[NB16 * 2][2];
 #pragma unroll
     for (int nb = 0; nb < NB16 * 2; ++nb) {
-      const float p0 = exp2f(s[nb][0] - mx[0]), p1 = exp2f(s[nb][1] - mx[0]);
-      const float p2 = exp2f(s[nb][2] - mx[1]), p3 = exp2f(s[nb][3] - mx[1]);
+      // exp2(s * scale - max): one FFMA + one MUFU per score
+      const float p0 = ex2_ftz(fmaf(s[nb][0], p.scale_log2, -mx[0])), p1 = ex2_ftz(fmaf(s[nb][1], p.scale_log2, -mx[0]));
+      const float p2 = ex2_ftz(fmaf(s[nb][2], p.scale_log2, -mx[1])), p3 = ex2_ftz(fmaf(s[nb][3], p.scale_log2, -mx[1]));
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
       __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
@@ -414,7 +419,7 @@ static uav_status_t launch_cross(const FaParams& p, int batch, cudaStream_t stre
   int gx = (num_sms() * 8 + batch * p.heads - 1) / (batch * p.heads);
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
-  dim3 grid(gx, batch * p.heads);
+  dim3 grid(gx * p.heads, batch);
   cross_attn_kernel<D, NB16><<<grid, FA_THREADS, smem, stream>>>(p);
   UAV_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
