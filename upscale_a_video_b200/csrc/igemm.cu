@@ -405,12 +405,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               sbias[et] = (p.bias != nullptr && n_base + et < p.n_out) ? __ldg(p.bias + n_base + et)
                                                                        : 0.f;
             }
+            constexpr int COLS_PER_HALF = OUT_TILE_N / 2;
+            constexpr int CHUNKS = COLS_PER_HALF / 32;
+            // residual operand: software-pipelined one chunk ahead, the first chunk BEFORE the wait for the
+            // accumulator, so the DRAM latency of these per-row 64-byte loads hides behind the main loop of the tile
+            // (short-K GEMMs spend one exposed latency per chunk otherwise)
+            uint4 rq_next[4];
+            auto load_res = [&](int c, uint4 (&dst)[4]) {
+              const int n0 = n_base + half * COLS_PER_HALF + c * 32;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                dst[g] = make_uint4(0, 0, 0, 0);
+                if (res != nullptr && n0 + g * 8 < p.n_out) dst[g] = ldg16(res + n0 + g * 8);
+              }
+            };
+            if constexpr (AUX) load_res(0, rq_next);
             if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             epi_bar_sync();
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            constexpr int COLS_PER_HALF = OUT_TILE_N / 2;
-            constexpr int CHUNKS = COLS_PER_HALF / 32;
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
               const int col0 = half * COLS_PER_HALF + c * 32;  // column inside the output tile
@@ -421,13 +434,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               if constexpr (AUX) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                  rq[g] = make_uint4(0, 0, 0, 0);
+                  rq[g] = rq_next[g];
                   vq[g] = make_uint4(0, 0, 0, 0);
                   if (cols_ok && n0 + g * 8 < p.n_out) {
-                    if (res != nullptr) rq[g] = ldg16(res + n0 + g * 8);
                     if (rv != nullptr) vq[g] = ldg16(rv + n0 + g * 8);
                   }
                 }
+                if (c + 1 < CHUNKS) load_res(c + 1, rq_next);
               }
               uint32_t a[32];
               tmem_ld_32x32(taddr + col0, a);
