@@ -163,13 +163,31 @@ def run_reference_arm(args):
     v = sum(vals) / len(vals)
     cb["value"] = v
     T = frames_for(args.gpus)
-    print(json.dumps({"impl": "reference", "metric": "upscaled frames/sec (30 DDIM steps, 320x576->4x)", "value": v,
+    _emit({"impl": "reference", "metric": "upscaled frames/sec (30 DDIM steps, 320x576->4x)", "value": v,
                       "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": 1000.0 * T / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "f32", "data": "synthetic, random-init weights",
                       "config": {"workload": f"{T}-frame 320x576->1280x2304, 30 DDIM steps, guidance 6 (CPU: bounded sample, FLOP-scaled)"},
                       "cpu_baseline": cb,
-                      "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on
+    communicator creation), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -181,6 +199,7 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=STEPS_DDIM, help=argparse.SUPPRESS)  # debugging only
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -316,7 +335,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
         if cb is not None:
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
