@@ -305,14 +305,15 @@ def main():
         burst = peaks.get("bf16_tflops", 1590.0)
         roof = {"bound": "tensor", "kernel": "uav::igemm_kernel (tcgen05 implicit GEMM: conv2d/conv_t/linear)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                # DRAM bytes of the representative launch below, from `ncu --set full` (profiles/r1_ncu_full_summaries.txt:
-                # 759.96 MB read + 719.35 MB written; algorithmic = 755 MB in + 755 MB out + 4.7 MB weights)
-                "traffic": 1479313920,
+                # DRAM bytes of the representative launch below, from `ncu --set full` of the CTA-pair kernel
+                # (profiles/r1_ncu_full_summaries_v2.txt: 759.96 MB read + 718.57 MB written; algorithmic = 755 MB in
+                # + 755 MB out + 4.7 MB weights)
+                "traffic": 1478523648,
                 "representative_launch": {"op": "conv3x3 512->512, 16 x 160x288 (3.48 TFLOP)", "ms": rep_ms,
                                           "achieved": rep_flops / rep_ms / 1e9, "peak_burst": burst,
                                           "frac_of_burst_peak": rep_flops / rep_ms / 1e9 / burst,
                                           "algorithmic_bytes": 2 * (16 * 160 * 288 * 512 * 2) + 512 * 9 * 512 * 2,
-                                          "ncu_tensor_pipe_active_pct": 85.05},
+                                          "ncu_tensor_pipe_active_pct": 81.06},
                 "peak_source": which, "launches_per_unet_forward": ig["launches"],
                 "share_of_unet_forward_time": ig["ms"] / tot_ms,
                 "per_kind_ms": {k: round(d["ms"], 3) for k, d in summ.items()},
