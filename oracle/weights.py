@@ -23,6 +23,12 @@ def make_tensor(key: str, shape: Sequence[int], seed: int) -> torch.Tensor:
     x = torch.randn(shape, generator=g, dtype=torch.float32)
     leaf = key.rsplit(".", 1)[-1]
     parent = key.rsplit(".", 2)[-2] if key.count(".") >= 1 else ""
+    if leaf == "running_var":  # BatchNorm statistics (RAFT context encoder): positive
+        return 0.5 + 0.5 * x.abs()
+    if leaf == "running_mean":
+        return 0.1 * x
+    if leaf == "num_batches_tracked":
+        return torch.zeros(shape, dtype=torch.long)
     is_norm = "norm" in parent
     if leaf == "bias":
         return x * 0.05

@@ -134,3 +134,34 @@ def test_color_oracle_against_reference_fixtures():
         # the CLI block end to end (inference_upscale_a_video.py:323-333)
         out = co.color_fix_frames(hr.permute(1, 0, 2, 3)[None], lr.permute(1, 0, 2, 3)[None], "Wavelet")
         assert (out - c["wavelet"]).abs().max().item() < 5e-6, name
+
+
+# ------------------------------------------------------------------------------------------------
+# RAFT bidirectional flow: oracle/raft_oracle.py vs the reference's own RAFT / RAFT_bi
+# ------------------------------------------------------------------------------------------------
+def test_raft_oracle_against_reference_fixtures():
+    from oracle import raft_oracle as R
+
+    g = _load("raft.pt")
+    shapes = json.load(open(os.path.join(G, "shapes_raft.json")))
+    assert len(shapes) == 179
+    sd = make_state_dict(shapes, g["seed"])
+    cases = g["cases"]
+    with torch.no_grad():
+        c = cases["raft_128x136_it3"]
+        clip = R.synth_clip(*c["clip"])
+        lo, up = R.raft_forward(sd, clip[0, :, 0][None], clip[0, :, 1][None], c["iters"])
+        # fp32 with the same ATen ops in the same order: only thread-count dependent reduction order differs
+        assert (lo - c["flow_lo"]).abs().max().item() < 1e-4 and (up - c["flow_up"]).abs().max().item() < 1e-3
+        assert c["flow_up"].abs().max().item() > 0.5  # the fixture is not a trivial zero flow
+        c = cases["bi_124x132_it2"]  # H, W not multiples of 8: trilinear resize in, resize_flow_pytorch (row quirk) out
+        f, b = R.raft_bi_forward(sd, R.synth_clip(*c["clip"]), c["iters"])
+        assert f.shape == (1, 2, 2, 124, 132)
+        st = c["stride"]
+        assert (f[..., ::st, ::st] - c["fwd"]).abs().max().item() < 1e-3 and (b[..., ::st, ::st] - c["bwd"]).abs().max().item() < 1e-3
+        c = cases["slicing_13f_128x128_it1"]  # 13 frames > one 12-frame short clip
+        f, b = R.raft_bi_forward_slicing(sd, R.synth_clip(*c["clip"]), c["iters"])
+        assert f.shape == (1, 2, 12, 128, 128)
+        st = c["stride"]
+        assert (f[..., ::st, ::st] - c["fwd"]).abs().max().item() < 1e-3 and (b[..., ::st, ::st] - c["bwd"]).abs().max().item() < 1e-3
+    assert [R.short_clip_len(w) for w in (576, 640, 641, 720, 960, 1280, 1281)] == [12, 12, 8, 8, 4, 4, 2]
