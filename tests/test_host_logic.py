@@ -142,3 +142,93 @@ def test_tile_plan_matches_reference_loop():
         exact = torch.equal(out, frame.repeat_interleave(4, -2).repeat_interleave(4, -1))
         assert exact == c["paste_exact"], (h, w, c["tile_size"])
     assert needs_tiling(320, 576) and not needs_tiling(180, 320)
+
+
+def test_ctypes_prototypes_match_header():
+    """every binding in _lib.py takes exactly as many arguments as its declaration in include/uav_b200.h, with pointers /
+    integers / floats in the same positions (an ABI drift here corrupts arguments silently instead of failing)"""
+    import ctypes as C
+    from upscale_a_video_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "uav_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    decls = dict(re.findall(r"\b(uav_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr))
+    assert len(decls) >= 30
+
+    def kind(param: str) -> str:
+        p = param.strip()
+        if "*" in p or p.startswith("uav_stream_t"):
+            return "ptr"
+        base = p.rsplit(" ", 1)[0].replace("const ", "").strip()
+        return {"float": "f32", "int": "i32", "int64_t": "i64", "size_t": "u64", "uint64_t": "u64",
+                "uint32_t": "u32"}[base]  # LP64
+
+    ck = {C.c_void_p: "ptr", C.c_int64: "i64", C.c_int: "i32", C.c_int32: "i32", C.c_float: "f32", C.c_size_t: "u64",
+          C.c_uint64: "u64", C.c_uint32: "u32"}
+    protos = dict(_lib._PROTOS)
+    protos.update({k: v[1] for k, v in _lib._SPECIAL.items()})
+    for name, params in decls.items():
+        plist = [] if params.strip() in ("", "void") else [kind(x) for x in params.split(",")]
+        got = [ck.get(t, "ptr") for t in protos[name]]  # POINTER(Epilogue) etc. count as pointers
+        assert got == plist, f"{name}: header {plist} vs ctypes {got}"
+
+
+TILE_WORKER = r"""
+import sys, types
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from upscale_a_video_b200 import tiling
+from upscale_a_video_b200.pipeline_upscale_a_video import randn_tensor
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+
+
+class StubPipe:
+    # nearest-x4 of the tile plus a signature of the noise / latents it was handed (the shared generator stream)
+    def __init__(self):
+        self.process_group = None
+        self.vae = types.SimpleNamespace(config=types.SimpleNamespace(latent_channels=4))
+        self.text_encoder = types.SimpleNamespace(dtype=torch.float32)
+        self.calls = 0
+
+    def __call__(self, image=None, flows_bi=None, noise=None, latents=None, **kw):
+        assert self.process_group is None or dist.get_world_size(self.process_group) == 1  # no nested sharding
+        self.calls += 1
+        up = image.repeat_interleave(4, -2).repeat_interleave(4, -1).float()
+        return types.SimpleNamespace(images=up + noise.mean() + 10.0 * latents.mean())
+
+
+h, w, t = 300, 600, 2  # 2 x 3 tiles of 256 (+64 overlap), last column merged
+image = torch.arange(3 * t * h * w, dtype=torch.float32).reshape(1, 3, t, h, w) / (3 * t * h * w)
+pipe = StubPipe()
+out = tiling.upscale_tiled(pipe, image, generator=torch.Generator().manual_seed(10))
+plan = tiling.plan_tiles(h, w)
+assert pipe.calls == len([i for i in range(len(plan)) if i % world == rank]) and pipe.process_group is None
+# serial re-statement with ONE generator consumed tile by tile, as the reference loop does
+g = torch.Generator().manual_seed(10)
+ref = torch.zeros(1, 3, t, 4 * h, 4 * w)
+for tl in plan:
+    y0, y1, x0, x1 = tl.in_box
+    tile = image[:, :, :, y0:y1, x0:x1]
+    noise = randn_tensor(tile.shape, generator=g, device="cpu", dtype=torch.float32)
+    lat = randn_tensor((1, 4, t, y1 - y0, x1 - x0), generator=g, device="cpu", dtype=torch.float32)
+    res = tile.repeat_interleave(4, -2).repeat_interleave(4, -1) + noise.mean() + 10.0 * lat.mean()
+    oy0, oy1, ox0, ox1 = tl.out_box
+    sy0, sy1, sx0, sx1 = tl.src_box
+    ref[:, :, :, oy0:oy1, ox0:ox1] = res[:, :, :, sy0:sy1, sx0:sx1]
+assert torch.equal(out, ref), (out - ref).abs().max()
+dist.barrier()
+if rank == 0:
+    print("TILES_OK", len(plan))
+"""
+
+
+def test_upscale_tiled_gloo_world2(tmp_path):
+    """the tile driver deals tiles round-robin to ranks, keeps the reference's single generator stream, never shards
+    windows inside a tile, and every rank ends with the full pasted output (one all_reduce)"""
+    script = tmp_path / "tile_worker.py"
+    script.write_text(TILE_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519", str(script), ROOT],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "TILES_OK" in r.stdout, r.stdout + r.stderr
