@@ -1,0 +1,283 @@
+"""emu_ops.py — plain-torch stand-ins for the kernel wrappers of `upscale_a_video_b200/ops.py` (TEST INFRASTRUCTURE).
+
+Each function re-states the CONTRACT of one wrapper (argument meaning, channels-last layouts, channel-slice views,
+`out=` placement, fused-epilogue order, fp32 math with ONE rounding to the fp16 output) so that the host logic of the
+package — weight packing, buffer plumbing, batching, caching, the module graph — can be exercised on a CPU-only box
+against the reference fixtures (`tests/test_host_emulated.py`).  The kernels themselves are validated on the GPU
+(`-m gpu`); the product never imports this file and keeps refusing CPU tensors (`_lib.require_cuda`), which the emulated
+tests stub explicitly."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+
+
+def _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype):
+    """acc: (..., N) fp32 pre-bias accumulators flattened over rows in the output's row order"""
+    n = acc.shape[-1]
+    v = acc.reshape(-1, n)
+    if bias is not None:
+        v = v + bias.float()
+    if rowvec is not None:
+        idx = torch.arange(v.shape[0]) // max(int(rows_per_vec), 1)
+        v = v + rowvec.float().reshape(-1, rowvec.shape[-1])[idx][:, :n]
+    if act == ACT_SILU:
+        v = F.silu(v)
+    elif act == ACT_GEGLU:
+        half = n // 2
+        v = v[:, :half] * F.gelu(v[:, half:])
+    if residual is not None:
+        v = v + residual.float().reshape(-1, residual.shape[-1])[:, :v.shape[-1]]
+    return v
+
+
+def _finish(v, lead_shape, out, out_dtype):
+    v = v.reshape(*lead_shape, v.shape[-1])
+    if out is None:
+        return v.to(out_dtype)
+    out.copy_(v)
+    return out
+
+
+def linear(a, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
+    acc = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
+    v = _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype)
+    return _finish(v, a.shape[:-1], out, out_dtype)
+
+
+def _conv_nhwc(x4, w, stride, pads):
+    """x4 (N, H, W, C) fp32, w (Cout, kh, kw, Cin); pads = (left, right, top, bottom)"""
+    xp = F.pad(x4.permute(0, 3, 1, 2), pads)
+    return F.conv2d(xp, w.float().permute(0, 3, 1, 2), stride=stride).permute(0, 2, 3, 1)
+
+
+def conv2d(x, w, bias=None, *, stride=1, pad_mode=0, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE,
+           out_dtype=torch.float16):
+    *lead, H, W, Cin = x.shape
+    k = w.shape[1]
+    x4 = x.float().reshape(-1, H, W, Cin)
+    if stride == 1:
+        p = k // 2
+        y = _conv_nhwc(x4, w, 1, (p, p, p, p))
+    elif pad_mode == 0:
+        y = _conv_nhwc(x4, w, 2, (1, 1, 1, 1))
+    else:  # F.pad (0, 1, 0, 1) then no padding
+        y = _conv_nhwc(x4, w, 2, (0, 1, 0, 1))
+    v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype)
+    return _finish(v, (*lead, y.shape[1], y.shape[2]), out, out_dtype)
+
+
+def collapse_upsample_filter(w):
+    from upscale_a_video_b200 import ops as real_ops  # pure torch math, no kernel involved
+    return real_ops.collapse_upsample_filter(w)
+
+
+def upsample2x_conv3x3(x, w4, bias=None):
+    """phase p = a*2+b -> output pixel (2y+a, 2x+b); taps read rows {y-1, y} (a=0) or {y, y+1} (a=1), columns likewise"""
+    *lead, H, W, Cin = x.shape
+    Cout = w4.shape[1]
+    x4 = x.float().reshape(-1, H, W, Cin)
+    out = torch.zeros(x4.shape[0], 2 * H, 2 * W, Cout)
+    for a in range(2):
+        for b in range(2):
+            pads = (1 - b, b, 1 - a, a)  # left, right, top, bottom
+            y = _conv_nhwc(x4, w4[a * 2 + b], 1, pads)
+            out[:, a::2, b::2] = y
+    if bias is not None:
+        out = out + bias.float()
+    return out.reshape(*lead, 2 * H, 2 * W, Cout).half()
+
+
+def conv_temporal(x, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
+    B, T, H, W, Cin = x.shape
+    Cout, k, _ = w.shape
+    xp = F.pad(x.float().permute(0, 4, 1, 2, 3), (0, 0, 0, 0, k // 2, k // 2))
+    y = F.conv3d(xp, w.float().permute(0, 2, 1)[:, :, :, None, None]).permute(0, 2, 3, 4, 1)
+    v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype)
+    return _finish(v, (B, T, H, W), out, out_dtype)
+
+
+def conv3d(x, w, bias=None, *, out=None, residual=None, act=ACT_NONE, out_dtype=torch.float16):
+    B, T, H, W, Cin = x.shape
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float().permute(0, 4, 1, 2, 3), padding=1).permute(0, 2, 3, 4, 1)
+    v = _epilogue(y, bias, None, 0, residual, act, out, out_dtype)
+    return _finish(v, (B, T, H, W), out, out_dtype)
+
+
+def group_norm(x, gamma, beta, groups, eps, *, silu, n_outer, out=None):
+    C = x.shape[-1]
+    v = x.float().reshape(n_outer, -1, C).permute(0, 2, 1)  # (n, C, pixels)
+    y = F.group_norm(v, groups, gamma.float(), beta.float(), eps)
+    if silu:
+        y = F.silu(y)
+    y = y.permute(0, 2, 1).reshape(x.shape)
+    if out is None:
+        return y.half()
+    out.copy_(y)
+    return out
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, out=None):
+    y = F.layer_norm(x.float(), (x.shape[-1],), gamma.float(), beta.float(), eps)
+    if out is None:
+        return y.half()
+    out.copy_(y)
+    return out
+
+
+def attention(q, k, v, heads, *, kv_batch_div=1, scale=None, out=None):
+    batch, nq, C = q.shape
+    d = C // heads
+    scale = d ** -0.5 if scale is None else scale
+    kk = k.float().repeat_interleave(kv_batch_div, dim=0).reshape(batch, -1, heads, d).permute(0, 2, 1, 3)
+    vv = v.float().repeat_interleave(kv_batch_div, dim=0).reshape(batch, -1, heads, d).permute(0, 2, 1, 3)
+    qq = q.float().reshape(batch, nq, heads, d).permute(0, 2, 1, 3)
+    p = torch.softmax(qq @ kk.transpose(-1, -2) * scale, dim=-1)
+    o = (p @ vv).permute(0, 2, 1, 3).reshape(batch, nq, C)
+    if out is None:
+        return o.half()
+    out.copy_(o)
+    return out
+
+
+def temporal_attention(q, k, v, heads, rot, bias, *, out=None):
+    """q, k, v (B, F, HW, heads*d); rot (F, 16, 2) cos / sin of frame * freq_pair; bias (heads, F, F); rotary on the first 32
+    dims of every head, interleaved pairs (x0, x1) -> (x0 c - x1 s, x1 c + x0 s)"""
+    B, Fr, HW, C = q.shape
+    d = C // heads
+
+    def seq(t):  # -> (B*HW, heads, F, d)
+        return t.float().permute(0, 2, 1, 3).reshape(B * HW, Fr, heads, d).permute(0, 2, 1, 3)
+
+    def rotary(t):
+        cos, sin = rot[:, :, 0].float(), rot[:, :, 1].float()  # (F, 16)
+        r = t[..., :32].reshape(*t.shape[:-1], 16, 2)
+        x0, x1 = r[..., 0], r[..., 1]
+        rr = torch.stack([x0 * cos - x1 * sin, x1 * cos + x0 * sin], dim=-1).reshape(*t.shape[:-1], 32)
+        return torch.cat([rr, t[..., 32:]], dim=-1)
+
+    qs, ks, vs = rotary(seq(q) * d ** -0.5), rotary(seq(k)).half().float(), seq(v)
+    p = torch.softmax(qs @ ks.transpose(-1, -2) + bias.float(), dim=-1)
+    o = (p @ vs).permute(0, 2, 1, 3).reshape(B, HW, Fr, C).permute(0, 2, 1, 3)
+    if out is None:
+        return o.half()
+    out.copy_(o)
+    return out
+
+
+def copy_channels(src, dst):
+    dst.copy_(src)
+    return dst
+
+
+def concat_channels(a, b):
+    if b.shape[0] == 1 and a.shape[0] > 1:
+        b = b.expand(a.shape[0], *b.shape[1:])
+    return torch.cat([a, b], dim=-1)
+
+
+def repeat_batch(x, n):
+    return x.repeat(n, *([1] * (x.dim() - 1)))
+
+
+def upsample_nearest(x, size=None):
+    *lead, H, W, C = x.shape
+    x4 = x.reshape(-1, H, W, C).permute(0, 3, 1, 2).float()
+    y = F.interpolate(x4, scale_factor=2, mode="nearest") if size is None else F.interpolate(x4, size=tuple(size), mode="nearest")
+    return y.permute(0, 2, 3, 1).reshape(*lead, y.shape[-2], y.shape[-1], C).to(x.dtype)
+
+
+def planar_to_channels_last(src, dst, c_off=0, scale=1.0):
+    dst[..., c_off:c_off + src.shape[1]] = (src.float() * scale).permute(0, 2, 3, 4, 1)
+    return dst
+
+
+def channels_last_to_planar(src, C, out_dtype, clamp=False):
+    y = src[..., :C].float().permute(0, 4, 1, 2, 3)
+    if clamp:
+        y = y.clamp(-1, 1)
+    return y.to(out_dtype).contiguous()
+
+
+def silu(x):
+    return F.silu(x.float()).half()
+
+
+def sft_fuse(dec, scale, shift, w):
+    d = dec.float()
+    return (d + w * (d * scale.float() + shift.float())).half()
+
+
+def timestep_embedding(t, dim, flip_sin_to_cos, freq_shift):
+    """diffusers.models.embeddings.get_timestep_embedding (max_period 10000, scale 1)"""
+    half = dim // 2
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
+    emb = t.float()[:, None] * torch.exp(exponent)[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+    return emb.half()
+
+
+# ---------------------------------------------------------------------------------------
+# sampler ops on the reference's "b c t h w" latents: torch op sequences (one rounding per op in the tensor dtype, which
+# is what the kernels replay)
+# ---------------------------------------------------------------------------------------
+def cfg_combine(pred2, guidance_scale):
+    u, t = pred2.chunk(2)
+    return u + guidance_scale * (t - u)
+
+
+def window_blend(dst, src, t0, covered_mask):
+    for k in range(src.shape[2]):
+        if (covered_mask >> k) & 1:
+            dst[:, :, t0 + k] = dst[:, :, t0 + k] * 0.5 + src[:, :, k] * 0.5
+        else:
+            dst[:, :, t0 + k] = src[:, :, k]
+    return dst
+
+
+def ddim_step_v0(model_output, sample, pred_type, sqrt_alpha, sqrt_beta, clip, clip_range):
+    if pred_type == 0:
+        r = (sample - sqrt_beta * model_output) * (1.0 / sqrt_alpha)
+    elif pred_type == 1:
+        r = model_output.clone()
+    else:
+        r = sqrt_alpha * sample - sqrt_beta * model_output
+    return r.clamp(-clip_range, clip_range) if clip else r
+
+
+def ddim_step_vt(x0, model_output, sample, pred_type, sqrt_alpha, sqrt_beta, sqrt_alpha_prev, dir_coef, clip, clip_range,
+                 std_dev=0.0, noise=None):
+    if pred_type == 0:
+        eps = model_output
+    elif pred_type == 1:
+        eps = (sample - sqrt_alpha * x0) * (1.0 / sqrt_beta)
+    else:
+        eps = sqrt_alpha * model_output + sqrt_beta * sample
+    if clip:
+        x0 = x0.clamp(-clip_range, clip_range)
+    r = sqrt_alpha_prev * x0 + dir_coef * eps
+    if noise is not None:
+        r = r + std_dev * noise
+    return r
+
+
+def add_noise(x, noise, sqrt_alpha, sqrt_one_minus_alpha):
+    return sqrt_alpha * x + sqrt_one_minus_alpha * noise
+
+
+def propagate_step(feat_prop, feat_cur, flow_prop, flow_check, out, *, nearest, fuse, fuse_scale, alpha1, alpha2,
+                   half_grid_sample):
+    """one recurrence step of Propagation.forward (propagation_module.py:234-254) on (C|2, H, W) planes of one frame"""
+    from oracle import uav_oracle as O
+    fp, fc = flow_prop[None].float(), flow_check[None].float()
+    mask = O.fb_consistency(fp, fc, alpha1, alpha2)
+    warped = O.flow_warp(feat_prop[None].float(), fp.permute(0, 2, 3, 1), "nearest" if nearest else "bilinear")
+    cur = feat_cur[None].float()
+    if fuse:
+        warped = warped * fuse_scale + cur * (1 - fuse_scale)
+    out.copy_((mask * warped + (1 - mask) * cur)[0])
+    return out

@@ -16,6 +16,13 @@ class UavError(RuntimeError):
     pass
 
 
+def require_cuda(t, who: str):
+    """every public entry of the package refuses non-CUDA tensors: there is no CPU path.  (A single choke point so that the
+    CPU test-suite can exercise the host logic against emulated kernels — tests/emu_ops.py — by stubbing exactly this.)"""
+    if not t.is_cuda:
+        raise UavError(f"{who}: CUDA tensors required — uav_b200 has no CPU path")
+
+
 class Epilogue(C.Structure):
     """uav_epilogue_t"""
     _fields_ = [

@@ -16,7 +16,7 @@ from torch import nn
 
 from . import ops
 from ._config import ConfigMixin
-from ._lib import UavError
+from . import _lib
 from .layers import (Ctx, DownEncoderBlock3D, Fuse_sft_block, InflatedConv3d, PackedModule, ResnetBlock3D_plus,
                      UNetMidBlock3D, UNetMidBlock3D_plus, UpDecoderBlock3D, UpDecoderBlock3D_plus, _gn)
 
@@ -172,8 +172,7 @@ class AutoencoderKLVideo(PackedModule, ConfigMixin):
 
     def _to_cl(self, x, pad_to=8, scale=1.0):
         """(b, c, t, h, w) fp16/fp32 -> zero-padded channels-last fp16 (b, t, h, w, 8)"""
-        if not x.is_cuda:
-            raise UavError("AutoencoderKLVideo: CUDA tensors required — uav_b200 has no CPU path")
+        _lib.require_cuda(x, "AutoencoderKLVideo")
         B, C, T, H, W = x.shape
         buf = torch.zeros(B, T, H, W, (C + pad_to - 1) // pad_to * pad_to, dtype=torch.float16, device=x.device)
         src = x if x.dtype in (torch.float16, torch.float32) else x.float()

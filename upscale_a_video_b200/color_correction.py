@@ -7,7 +7,7 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 __all__ = ["calc_mean_std", "adaptive_instance_normalization", "adain_color_fix", "wavelet_blur", "wavelet_decomposition",
            "wavelet_reconstruction", "wavelet_color_fix", "upsample_lr_frames", "color_fix_frames", "pack_video_uint8"]
@@ -16,8 +16,7 @@ __all__ = ["calc_mean_std", "adaptive_instance_normalization", "adain_color_fix"
 def _check(x: torch.Tensor, name: str):
     if x.dim() != 4:
         raise AssertionError("The input feature should be 4D tensor.")  # color_correction.py:53
-    if not x.is_cuda:
-        raise RuntimeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    _lib.require_cuda(x, name)
 
 
 def calc_mean_std(feat: torch.Tensor, eps: float = 1e-5):

@@ -19,7 +19,7 @@ from typing import Any, List, Optional, Union
 
 import torch
 
-from . import ops, sharding
+from . import _lib, ops, sharding
 from ._config import ConfigMixin
 from ._lib import UavError
 
@@ -185,8 +185,7 @@ class VideoUpscalePipeline(ConfigMixin):
         else:
             batch_size = prompt_embeds.shape[0]
         device = self._execution_device
-        if device.type != "cuda":
-            raise UavError("VideoUpscalePipeline: models must be on a CUDA device — uav_b200 has no CPU path")
+        _lib.require_cuda(torch.empty(0, device=device), "VideoUpscalePipeline (models must be on a CUDA device)")
         do_cfg = guidance_scale > 1.0
         prompt_embeds = self._encode_prompt(prompt, device, num_images_per_prompt, do_cfg, negative_prompt,
                                             prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds)

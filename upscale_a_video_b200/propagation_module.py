@@ -14,6 +14,7 @@ import torch
 from torch import nn
 
 from . import ops
+from . import _lib
 from ._lib import UavError
 
 # How torch's CUDA grid_sampler treats fp16 inputs (see csrc/sampler.cu): 0 = opmath/fp32 intermediates.
@@ -34,8 +35,7 @@ class Propagation(nn.Module):
     def forward(self, x, flows_forward, flows_backward, interpolation="bilinear", mode="fuse", fuse_scale=0.5,
                 alpha1=0.01, alpha2=0.5):
         """x: (b, c, t, h, w); flows: (b, 2, t-1, h, w), same dtype/device as x.  Returns (b, c, t, h, w)."""
-        if not x.is_cuda:
-            raise UavError("Propagation: CUDA tensors required (there is no CPU path)")
+        _lib.require_cuda(x, "Propagation")
         b, c, t, h, w = x.shape
         if tuple(flows_forward.shape[2:]) != (t - 1, h, w) or tuple(flows_backward.shape[2:]) != (t - 1, h, w):
             # the reference area-resizes the flows (propagation_module.py:206-209); the pipeline always passes

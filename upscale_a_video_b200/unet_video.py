@@ -24,6 +24,7 @@ from torch import nn
 
 from . import ops
 from ._config import ConfigMixin
+from . import _lib
 from ._lib import UavError
 from .layers import (CrossAttention, CrossAttnDownBlock3D, CrossAttnUpBlock3D, Ctx, DownBlock3D, EmptyTemporalModule3D,
                      InflatedConv3d, PackedModule, ResnetBlock3D, RotaryEmbedding, TemporalModule3D,
@@ -215,8 +216,7 @@ class UNetVideoModel(PackedModule, ConfigMixin):
         classifier-free-guidance halves of the SAME latents / LR frames / noise level (pipeline...:614,551), so everything
         before the first text-conditioned layer (conv_in, down block 0, its temporal module, the first resnet of down
         block 1) is identical for both and is computed once (SURVEY.md §7.2 iii: exact work removal, ~3.6 % of the FLOPs)."""
-        if not sample.is_cuda:
-            raise UavError("UNetVideoModel.forward: CUDA tensors required — uav_b200 has no CPU path")
+        _lib.require_cuda(sample, "UNetVideoModel.forward")
         if attention_mask is not None:
             raise NotImplementedError("attention_mask is never passed by VideoUpscalePipeline")
         if encoder_hidden_states is None:
