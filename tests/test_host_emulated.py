@@ -122,3 +122,47 @@ def test_pipeline_host_logic_vs_golden(emulated, unet_sd, case):
     e_lat, e_img = _rel(lat, c["latents_out"]), _rel(out, c["out"])
     print(f"\n[pipeline host-emulated {case}] rel L2 err: latents {e_lat:.3e}, frames {e_img:.3e}")
     assert e_lat < 5e-2 and e_img < 5e-2  # same band as the GPU test
+
+
+def test_unet_host_logic_odd_shape_vs_oracle(emulated, unet_sd):
+    """a shape the fixtures do not hold: 5 frames, 18x20 (18 -> 9 -> 5 -> 3: odd sizes on the way down, explicit upsample sizes
+    on the way up) against the fp32 oracle (itself pinned to the reference by the fixtures)"""
+    from oracle import uav_oracle as O
+    cfg = json.load(open(os.path.join(CFG, "unet_video_config.json")))
+    m = _unet(unet_sd)
+    g = torch.Generator().manual_seed(3)
+    sample, low = torch.randn(2, 4, 5, 18, 20, generator=g), torch.randn(2, 3, 5, 18, 20, generator=g)
+    ctx = torch.randn(2, 77, 1024, generator=g) * 0.3
+    with torch.no_grad():
+        ref = O.unet_forward(unet_sd, cfg, sample, torch.tensor(500), low, ctx, torch.tensor([120]))
+    out = m(sample.half(), 500, low.half(), encoder_hidden_states=ctx.half(), class_labels=torch.tensor([120])).sample
+    assert _rel(out, ref) < 5e-3
+
+
+def test_pipeline_host_logic_long_clip_vs_oracle(emulated, unet_sd):
+    """17 frames (windows (0,8), (6,14), re-anchored (9,17)), the conditioned video VAE, propagation at both steps, 6 decode
+    chunks — against the oracle's restatement of VideoUpscalePipeline.__call__ in fp32"""
+    import bench
+    from oracle import uav_oracle as O
+    from oracle.weights import make_state_dict
+    from upscale_a_video_b200 import DDIMScheduler, DDPMScheduler, Propagation, VideoUpscalePipeline
+    meta = json.load(open(os.path.join(G, "meta.json")))
+    scfg = meta["sched_cfgs"]["v_scaled_offset"]
+    T, H, W, steps, prop = 17, 8, 8, 2, [0, 1]
+    image, fw, bw, pe = bench.synth_inputs(T, H, W, "cpu")
+    g = torch.Generator().manual_seed(5)
+    noise, lat0 = torch.randn(1, 3, T, H, W, generator=g), torch.randn(1, 4, T, H, W, generator=g)
+    pipe = VideoUpscalePipeline(None, None, DDPMScheduler(beta_schedule="scaled_linear"), DDIMScheduler(**scfg), _vae("vae_video"),
+                                _unet(unet_sd), Propagation(4, learnable=False))
+    neg, pos = pe.half().chunk(2)
+    out, lat = pipe(None, image=image, flows_bi=[fw, bw], num_inference_steps=steps, guidance_scale=6.0, noise_level=120,
+                    prompt_embeds=pos, negative_prompt_embeds=neg, latents=lat0, noise=noise, propagation_steps=prop,
+                    return_dict=False)
+    ucfg = json.load(open(os.path.join(CFG, "unet_video_config.json")))
+    vcfg = json.load(open(os.path.join(CFG, "vae_video_config.json")))
+    vsd = make_state_dict(json.load(open(os.path.join(G, "shapes_vae_video.json"))), meta["seed_vae"])
+    with torch.no_grad():
+        ref, ref_lat = O.pipeline_call(unet_sd, ucfg, vsd, vcfg, O.DDIM(**scfg), O.DDIM(beta_schedule="scaled_linear"), image=image,
+                                       prompt_embeds=pe, noise=noise, latents=lat0, flows_bi=[fw, bw], num_inference_steps=steps,
+                                       guidance_scale=6.0, noise_level=120, propagation_steps=prop, return_latents=True)
+    assert _rel(lat, ref_lat) < 5e-2 and _rel(out, ref) < 5e-2
