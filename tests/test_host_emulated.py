@@ -166,3 +166,73 @@ def test_pipeline_host_logic_long_clip_vs_oracle(emulated, unet_sd):
                                        prompt_embeds=pe, noise=noise, latents=lat0, flows_bi=[fw, bw], num_inference_steps=steps,
                                        guidance_scale=6.0, noise_level=120, propagation_steps=prop, return_latents=True)
     assert _rel(lat, ref_lat) < 5e-2 and _rel(out, ref) < 5e-2
+
+
+SHARD_WORKER = r"""
+import json, os, sys
+root = sys.argv[1]
+sys.path[:0] = [root, os.path.join(root, "tests")]
+import torch, torch.distributed as dist
+import bench, emu_ops
+from oracle.weights import make_state_dict
+from upscale_a_video_b200 import (_lib, autoencoder_kl_cond_video, layers, pipeline_upscale_a_video, propagation_module,
+                                  scheduling_ddim, unet_video)
+for mod in (layers, unet_video, autoencoder_kl_cond_video, pipeline_upscale_a_video, propagation_module, scheduling_ddim):
+    if hasattr(mod, "ops"):
+        mod.ops = emu_ops
+_lib.require_cuda = lambda t, who: None
+from upscale_a_video_b200 import AutoencoderKLVideo, DDIMScheduler, DDPMScheduler, Propagation, UNetVideoModel, VideoUpscalePipeline
+torch.set_num_threads(4)
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+solo = [dist.new_group([r]) for r in range(world)][rank]
+G, CFG = os.path.join(root, "tests", "golden"), os.path.join(root, "upscale_a_video_b200", "configs")
+meta = json.load(open(os.path.join(G, "meta.json")))
+unet = UNetVideoModel.from_config(json.load(open(os.path.join(CFG, "unet_video_config.json"))))
+unet.load_state_dict(make_state_dict(json.load(open(os.path.join(G, "shapes_unet.json"))), meta["seed_unet"]), strict=True)
+vae = AutoencoderKLVideo.from_config(json.load(open(os.path.join(CFG, "vae_3d_config.json"))))
+vae.load_state_dict(make_state_dict(json.load(open(os.path.join(G, "shapes_vae_3d.json"))), meta["seed_vae"]), strict=True)
+pipe = VideoUpscalePipeline(None, None, DDPMScheduler(beta_schedule="scaled_linear"),
+                            DDIMScheduler(**meta["sched_cfgs"]["v_scaled_offset"]), vae.eval(), unet.half().eval(),
+                            Propagation(4, learnable=False))
+T, H, W = 14, 8, 8  # two unique windows per step, five decode chunks (3 + 2 per rank, ragged last chunk)
+image, fw, bw, pe = bench.synth_inputs(T, H, W, "cpu")
+g = torch.Generator().manual_seed(5)
+noise, lat0 = torch.randn(1, 3, T, H, W, generator=g), torch.randn(1, 4, T, H, W, generator=g)
+neg, pos = pe.half().chunk(2)
+kw = dict(image=image, flows_bi=[fw, bw], num_inference_steps=2, guidance_scale=6.0, noise_level=120, prompt_embeds=pos,
+          negative_prompt_embeds=neg, latents=lat0, noise=noise, propagation_steps=[1], return_dict=False)
+calls = {"n": 0}
+orig_forward = unet.forward
+def counting(*a, **k):
+    calls["n"] += 1
+    return orig_forward(*a, **k)
+unet.forward = counting
+pipe.process_group = solo
+out1, lat1 = pipe(None, **kw)
+n_solo = calls["n"]
+calls["n"] = 0
+pipe.process_group = None
+out2, lat2 = pipe(None, **kw)
+assert n_solo == 4 and calls["n"] == 2, (n_solo, calls["n"])  # 2 windows x 2 steps alone, 1 window x 2 steps when sharded
+assert torch.equal(lat1, lat2) and torch.equal(out1, out2), ((lat1 - lat2).abs().max(), (out1 - out2).abs().max())
+dist.barrier()
+if rank == 0:
+    print("SHARDED_PIPELINE_OK")
+"""
+
+
+def test_sharded_pipeline_gloo_world2(tmp_path):
+    """the whole N > 1 data path on CPU: two ranks (gloo) run VideoUpscalePipeline.__call__ with emulated kernels; windows of a
+    DDIM step and decode chunks are dealt to ranks, gathered once per step / once at the end, and every rank ends with a
+    result bit-identical to its own unsharded run (half the UNet calls)"""
+    import subprocess
+    import sys
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29523", str(script), root], capture_output=True, text=True, env=env,
+                       timeout=1500)
+    assert r.returncode == 0 and "SHARDED_PIPELINE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
