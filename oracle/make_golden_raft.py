@@ -61,6 +61,11 @@ def main():
         clip = synth_clip(13, 128, 128, 3)
         f, b = ref_bi.RAFT_bi.forward_slicing(holder, clip, iters=1)
         cases["slicing_13f_128x128_it1"] = {"clip": [13, 128, 128, 3], "iters": 1, "stride": 4, "fwd": f[..., ::4, ::4].clone(), "bwd": b[..., ::4, ::4].clone()}
+        # (d) one pair at the BASELINE.json frame size (320x576 -> 40x72 grid, 2880^2 correlation volume), every 8th pixel stored
+        clip = synth_clip(2, 320, 576, 4)
+        lo, up = model(clip[0, :, 0][None], clip[0, :, 1][None], iters=4, test_mode=True)
+        cases["raft_320x576_it4"] = {"clip": [2, 320, 576, 4], "iters": 4, "stride": 8, "flow_lo": lo,
+                                     "flow_up": up[..., ::8, ::8].clone()}
     torch.save({"seed": SEED, "cases": cases}, os.path.join(OUT, "raft.pt"))
     print("wrote raft.pt", os.path.getsize(os.path.join(OUT, "raft.pt")), "bytes;", len(shapes), "tensors in the state dict")
 

@@ -164,4 +164,9 @@ def test_raft_oracle_against_reference_fixtures():
         assert f.shape == (1, 2, 12, 128, 128)
         st = c["stride"]
         assert (f[..., ::st, ::st] - c["fwd"]).abs().max().item() < 1e-3 and (b[..., ::st, ::st] - c["bwd"]).abs().max().item() < 1e-3
+        c = cases["raft_320x576_it4"]  # BASELINE frame size
+        clip = R.synth_clip(*c["clip"])
+        lo, up = R.raft_forward(sd, clip[0, :, 0][None], clip[0, :, 1][None], c["iters"])
+        st = c["stride"]
+        assert (lo - c["flow_lo"]).abs().max().item() < 1e-3 and (up[..., ::st, ::st] - c["flow_up"]).abs().max().item() < 1e-2
     assert [R.short_clip_len(w) for w in (576, 640, 641, 720, 960, 1280, 1281)] == [12, 12, 8, 8, 4, 4, 2]
