@@ -170,3 +170,17 @@ def test_raft_oracle_against_reference_fixtures():
         st = c["stride"]
         assert (lo - c["flow_lo"]).abs().max().item() < 1e-3 and (up[..., ::st, ::st] - c["flow_up"]).abs().max().item() < 1e-2
     assert [R.short_clip_len(w) for w in (576, 640, 641, 720, 960, 1280, 1281)] == [12, 12, 8, 8, 4, 4, 2]
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text encoder: oracle/clip_oracle.py vs transformers' CLIPTextModel
+# ------------------------------------------------------------------------------------------------
+def test_clip_oracle_against_transformers_fixtures():
+    from oracle import clip_oracle as Co
+
+    g = _load("clip.pt")
+    for name, c in g["cases"].items():
+        sd = make_state_dict(c["shapes"], g["seed"])
+        with torch.no_grad():
+            out = Co.clip_text_forward(sd, c["config"], c["input_ids"])
+        assert (out[..., ::c["col_stride"]] - c["last_hidden_state"]).abs().max().item() < 2e-5, name
