@@ -281,3 +281,36 @@ def propagate_step(feat_prop, feat_cur, flow_prop, flow_check, out, *, nearest, 
         warped = warped * fuse_scale + cur * (1 - fuse_scale)
     out.copy_((mask * warped + (1 - mask) * cur)[0])
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# post-decode colour fix + packing (csrc/postprocess.cu): planar fp32 "t c h w" frames
+# ---------------------------------------------------------------------------------------
+def bicubic_upsample(x, scale=4):
+    return F.interpolate(x.float(), scale_factor=scale, mode="bicubic")
+
+
+def plane_stats(x, eps=1e-5):
+    x = x.float()
+    t, c = x.shape[:2]
+    v = x.reshape(t, c, -1)
+    return v.mean(-1).reshape(t, c, 1, 1), (v.var(-1) + eps).sqrt().reshape(t, c, 1, 1)
+
+
+def adain_apply(content, c_mean, c_std, s_mean, s_std):
+    return (content.float() - c_mean) / c_std * s_std + s_mean
+
+
+def wavelet_level(image, radius, *, low=None, high=None, high_first=False, add=None):
+    from oracle import color_oracle as co
+    blur = co.wavelet_blur(image, radius)
+    if high is not None:
+        d = image - blur
+        high.copy_(d if high_first else high + d)
+    if low is not None:
+        low.copy_(blur if add is None else add + blur)
+
+
+def pack_video_uint8(frames):
+    v = (frames.float() / 2 + 0.5).clamp(0, 1) * 255
+    return v.permute(0, 2, 3, 1).contiguous().to(torch.int32).to(torch.uint8)

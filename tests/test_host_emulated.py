@@ -236,3 +236,25 @@ def test_sharded_pipeline_gloo_world2(tmp_path):
                         "127.0.0.1", "--master-port", "29523", str(script), root], capture_output=True, text=True, env=env,
                        timeout=1500)
     assert r.returncode == 0 and "SHARDED_PIPELINE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_color_correction_host_logic_vs_reference_fixtures(monkeypatch):
+    """color_correction.py (AdaIN, wavelet chains with their ping-pong buffers, the CLI block, packing) with emulated kernels
+    against the fixtures minted from the reference's own functions"""
+    from upscale_a_video_b200 import _lib, color_correction as cc
+    monkeypatch.setattr(cc, "ops", emu_ops)
+    monkeypatch.setattr(_lib, "require_cuda", lambda t, who: None)
+    cases = torch.load(os.path.join(G, "color.pt"), map_location="cpu", weights_only=False)
+    for name, c in cases.items():
+        lr, hr, up = c["lr"], c["hr"], c["bicubic"]
+        assert (cc.upsample_lr_frames(lr, 4) - up).abs().max().item() < 2e-6
+        assert (cc.adaptive_instance_normalization(hr, up) - c["adain"]).abs().max().item() < 5e-6, name
+        assert (cc.wavelet_reconstruction(hr, up) - c["wavelet"]).abs().max().item() < 2e-6, name
+        if "high" in c:
+            high, low = cc.wavelet_decomposition(hr)
+            assert (high - c["high"]).abs().max().item() < 2e-6 and (low - c["low"]).abs().max().item() < 1e-6
+        out = cc.color_fix_frames(hr.permute(1, 0, 2, 3)[None], lr.permute(1, 0, 2, 3)[None], "AdaIn")
+        assert (out - c["adain"]).abs().max().item() < 1e-5
+        assert torch.equal(cc.pack_video_uint8(hr), c["pack_hr"])
+    with pytest.raises(ValueError):
+        cc.color_fix_frames(hr.permute(1, 0, 2, 3)[None], lr.permute(1, 0, 2, 3)[None], "bogus")
