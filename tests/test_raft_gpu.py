@@ -50,6 +50,21 @@ def test_raft_forward_against_reference_fixture():
     assert mean_up < 0.05 and max_up < 0.5
 
 
+def test_raft_forward_baseline_size():
+    """one pair at the BASELINE.json frame size: 40x72 grid, 2880 x 2880 correlation volume"""
+    from oracle import raft_oracle as R
+    m, sd, cases = _model()
+    c = cases["raft_320x576_it4"]
+    clip = R.synth_clip(*c["clip"])
+    lo, up = m(clip[0, :, 0][None].cuda(), clip[0, :, 1][None].cuda(), iters=c["iters"], test_mode=True)
+    st = c["stride"]
+    mean_lo, max_lo = _epe(lo, c["flow_lo"])
+    mean_up, max_up = _epe(up[..., ::st, ::st], c["flow_up"])
+    print(f"[raft] 320x576 it4: EPE lo mean {mean_lo:.4f} max {max_lo:.4f}; up mean {mean_up:.4f} max {max_up:.4f} px "
+          f"(flow magnitude mean {c['flow_up'].abs().mean().item():.1f} px)")
+    assert mean_up < 0.05 and max_up < 0.5
+
+
 def test_raft_bi_against_reference_fixtures():
     from oracle import raft_oracle as R
     from upscale_a_video_b200.raft import RAFT_bi

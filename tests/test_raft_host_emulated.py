@@ -130,6 +130,15 @@ def test_raft_host_logic_against_reference_fixtures(emu):
     print(f"[raft host, fp16-emulated kernels] EPE lo mean {mean_lo:.4f} max {max_lo:.4f}; up mean {mean_up:.4f} max {max_up:.4f} px")
     assert mean_up < 0.05 and max_up < 0.5 and mean_lo < 0.01 and max_lo < 0.1
 
+    c = g["cases"]["raft_320x576_it4"]  # BASELINE frame size
+    clip = R.synth_clip(*c["clip"])
+    with torch.no_grad():
+        lo, up = m._forward_impl(clip[0, :, 0][None], clip[0, :, 1][None], c["iters"], None)
+    st = c["stride"]
+    mean_up, max_up = _epe(up[..., ::st, ::st], c["flow_up"])
+    print(f"[raft host 320x576] EPE up mean {mean_up:.4f} max {max_up:.4f} px")
+    assert mean_up < 0.05 and max_up < 0.5
+
     # RAFT_bi: both directions in one batched call, non-multiple-of-8 size (resize in, row-quirk resize out)
     bi = emu.RAFT_bi(model_path=None, device="cpu")
     bi.fix_raft = m
