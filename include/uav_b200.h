@@ -41,7 +41,9 @@ typedef enum {
   UAV_ACT_GEGLU = 2,
   UAV_ACT_RELU = 3,    /* RAFT encoders / motion encoder / heads */
   UAV_ACT_SIGMOID = 4, /* RAFT SepConvGRU z, r gates */
-  UAV_ACT_TANH = 5     /* RAFT SepConvGRU candidate state */
+  UAV_ACT_TANH = 5,    /* RAFT SepConvGRU candidate state */
+  UAV_ACT_GELU = 6,    /* CLIP text encoder MLP, hidden_act "gelu" (exact erf form) */
+  UAV_ACT_QUICK_GELU = 7 /* CLIP text encoder MLP, hidden_act "quick_gelu": x * sigmoid(1.702 x) */
 } uav_act_t;
 
 typedef void* uav_stream_t; /* cudaStream_t */
@@ -297,6 +299,14 @@ uav_status_t uav_raft_flow_update(float* coords1, const float* delta, int64_t ld
  * [images][2][8*h8][8*w8] */
 uav_status_t uav_raft_convex_upsample(const float* coords1, const void* mask, int64_t ld_mask, int64_t nimg, int64_t h8,
                                       int64_t w8, float* out, uav_stream_t stream);
+
+/* ---- CLIP text encoder ---------------------------------------------------------------
+ * causal self-attention over a short sequence (transformers CLIPAttention under CLIPTextTransformer's causal mask):
+ * q, k, v, out fp16 [batch][n][ld] with `heads * head_dim` used columns (column slices of a fused qkv buffer allowed),
+ * n <= 128, head_dim <= 128 and even; out[i] = softmax_j<=i(scale * q_i . k_j) v_j */
+uav_status_t uav_attention_causal(const void* q, const void* k, const void* v, void* out, int64_t batch, int heads, int head_dim,
+                                  int64_t n, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale,
+                                  uav_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ _PROTOS = {
     "uav_raft_gru_update": [P, I64, P, I64, P, I64, I64, I64, P],
     "uav_raft_flow_update": [P, P, I64, I64, I64, I64, P, I64, P, I64, P, I64, P],
     "uav_raft_convex_upsample": [P, P, I64, I64, I64, I64, P, P],
+    "uav_attention_causal": [P, P, P, P, I64, I32, I32, I64, I64, I64, I64, I64, F32, P],
     "uav_bicubic_upsample": [P, I64, I64, I64, I32, P, P],
     "uav_plane_stats": [P, I64, I64, F32, P, P, P, P],
     "uav_adain_apply": [P, I64, I64, P, P, P, P, P, P],

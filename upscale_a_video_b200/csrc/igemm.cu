@@ -142,6 +142,8 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case UAV_ACT_RELU: return fmaxf(x, 0.f);
     case UAV_ACT_SIGMOID: return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x));
     case UAV_ACT_TANH: return 1.0f - 2.0f * rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x));
+    case UAV_ACT_GELU: return gelu_erf_f(x);
+    case UAV_ACT_QUICK_GELU: return x * rcp_ftz(1.0f + ex2_ftz(-2.4554669595930156f * x));  // x * sigmoid(1.702 x)
     default: return x;
   }
 }
@@ -844,7 +846,7 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   UAV_REQUIRE(p.ld_out >= p.n_out, "igemm: ld_out (%lld) < output columns (%d)",
               (long long)p.ld_out, p.n_out);
   UAV_REQUIRE(e->out_dtype == UAV_F16 || e->out_dtype == UAV_F32, "igemm: bad out_dtype");
-  UAV_REQUIRE(e->act >= UAV_ACT_NONE && e->act <= UAV_ACT_TANH, "igemm: bad activation");
+  UAV_REQUIRE(e->act >= UAV_ACT_NONE && e->act <= UAV_ACT_QUICK_GELU, "igemm: bad activation");
   if (p.num_tiles == 0) return UAV_OK;
 
   // TMA-store epilogue (smem-staged, fully coalesced, clips partial tiles) whenever the output

@@ -680,3 +680,26 @@ def raft_convex_upsample(coords1: torch.Tensor, mask: torch.Tensor, nimg: int, h
     _lib.check(lib.uav_raft_convex_upsample(coords1.data_ptr(), mask.data_ptr(), mask.stride(0), nimg, h8, w8, out.data_ptr(),
                                             _stream()), "uav_raft_convex_upsample")
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# CLIP text encoder: causal attention over the 77-token prompt, GELU epilogues
+# ---------------------------------------------------------------------------------------
+ACT_GELU, ACT_QUICK_GELU = 6, 7
+
+
+def attention_causal(q, k, v, heads: int, *, scale: Optional[float] = None, out=None):
+    """q, k, v: (batch, n, heads*d) fp16 (column slices of a fused qkv buffer allowed), n <= 128"""
+    batch, n, Cc = q.shape
+    d = Cc // heads
+    if out is None:
+        out = torch.empty(batch, n, Cc, dtype=torch.float16, device=q.device)
+    if scale is None:
+        scale = d ** -0.5
+    for t in (q, k, v, out):
+        assert t.is_cuda and t.dtype == torch.float16 and t.stride(-1) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    lib = _lib.load()
+    _lib.check(lib.uav_attention_causal(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, d, n,
+                                        q.stride(1), k.stride(1), v.stride(1), out.stride(1), scale, _stream()),
+               "uav_attention_causal")
+    return out
