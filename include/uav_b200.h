@@ -35,7 +35,16 @@ typedef enum {
 } uav_status_t;
 
 typedef enum { UAV_F16 = 0, UAV_F32 = 1 } uav_dtype_t;
-typedef enum { UAV_ACT_NONE = 0, UAV_ACT_SILU = 1, UAV_ACT_GEGLU = 2 } uav_act_t;
+typedef enum {
+  UAV_ACT_NONE = 0,
+  UAV_ACT_SILU = 1,
+  UAV_ACT_GEGLU = 2,
+  UAV_ACT_RELU = 3,    /* RAFT encoders / motion encoder / heads */
+  UAV_ACT_SIGMOID = 4, /* RAFT SepConvGRU z, r gates */
+  UAV_ACT_TANH = 5,    /* RAFT SepConvGRU candidate state */
+  UAV_ACT_GELU = 6,    /* CLIP text encoder MLP, hidden_act "gelu" (exact erf form) */
+  UAV_ACT_QUICK_GELU = 7 /* CLIP text encoder MLP, hidden_act "quick_gelu": x * sigmoid(1.702 x) */
+} uav_act_t;
 
 typedef void* uav_stream_t; /* cudaStream_t */
 
@@ -85,6 +94,15 @@ uav_status_t uav_conv2d(const void* x, int64_t NB, int64_t H, int64_t W, int64_t
                         int64_t ld_in, const void* w, int64_t Cout, int ksize, int stride,
                         int pad_mode, void* out, const uav_epilogue_t* epi,
                         uav_stream_t stream);
+
+/* stride-1 "same"-size convolution with an arbitrary kh x kw tap window (kh * kw <= 49) and asymmetric zero padding
+ * (pad_top rows above / pad_left columns left; the rest below / right): output [NB][H][W][ld_out].
+ * Used by the RAFT path: 7x7 convf1 (update.py:84), the 1x5 / 5x1 SepConvGRU convs (update.py:36-41) and, on
+ * space-to-depth inputs, the stride-2 convs of the encoders (extractor.py:10,44,136: a k x k stride-2 conv is a
+ * ceil(k/2) x ceil(k/2) stride-1 conv over the 2x2-phase-stacked input).  w: fp16 [Cout][kh][kw][Cin]. */
+uav_status_t uav_conv2d_taps(const void* x, int64_t NB, int64_t H, int64_t W, int64_t Cin, int64_t ld_in,
+                             const void* w, int64_t Cout, int kh, int kw, int pad_top, int pad_left, void* out,
+                             const uav_epilogue_t* epi, uav_stream_t stream);
 
 /* Temporal (k,1,1) convolution with zero padding (k-1)/2 in t (nn.Conv3d in
  * ResnetBlock3DCNN, resnet.py:332,348,361).  x: fp16 [B][T][HW][ld_in];
@@ -243,6 +261,51 @@ uav_status_t uav_wavelet_level(const float* image, int64_t planes, int64_t H, in
 /* (frames / 2 + 0.5).clamp(0, 1) * 255 -> "t h w c" -> uint8 by truncation (inference_upscale_a_video.py:354-356).
  * frames: [T][C][H][W] fp32, out: [T][H][W][C] uint8, C <= 4. Bit-exact. */
 uav_status_t uav_pack_video_uint8(const float* frames, int64_t T, int64_t C, int64_t H, int64_t W, uint8_t* out,
+                                  uav_stream_t stream);
+
+/* ---- RAFT bidirectional optical flow (models_video/RAFT) -----------------------------
+ * Non-GEMM kernels; activations channels-last fp16 [pixel][C], correlation volume / coordinates / flows fp32. */
+
+/* nn.InstanceNorm2d defaults (no affine, biased variance) + optional ReLU (extractor.py:27-31,49-50,129-130,176-178).
+ * x, y: [n][hw][C] fp16, C % 8 == 0.  Deterministic.  workspace: uav_instnorm_workspace_bytes(n, C) bytes. */
+size_t uav_instnorm_workspace_bytes(int64_t n, int64_t C);
+uav_status_t uav_instnorm_relu(const void* x, int64_t n, int64_t hw, int64_t C, float eps, int relu, void* y, void* workspace,
+                               uav_stream_t stream);
+/* y = relu(a + b) over n fp16 elements (ResidualBlock tail, extractor.py:57) */
+uav_status_t uav_add_relu(const void* a, const void* b, void* y, int64_t n, uav_stream_t stream);
+/* net = tanh(cnet[:, :C]) -> net[rows][ld_net]; inp = relu(cnet[:, C:2C]) -> inp_a (and inp_b if not NULL) (raft.py:117-120) */
+uav_status_t uav_raft_split_tanh_relu(const void* cnet, int64_t rows, int64_t C, void* net, int64_t ld_net, void* inp_a,
+                                      int64_t ld_a, void* inp_b, int64_t ld_b, uav_stream_t stream);
+/* F.avg_pool2d(x, 2, stride=2) on [planes][h][w] fp32 (corr.py:24-27) */
+uav_status_t uav_avgpool2x2_f32(const float* in, int64_t planes, int64_t h, int64_t w, float* out, uav_stream_t stream);
+/* CorrBlock.__call__ (corr.py:30-50), radius 4, 4 levels: levels[i] = [pixels][hs[i]][ws[i]] fp32 (one plane per query
+ * pixel), coords = [pixels][2] (x, y) at level 0; out fp16 [pixels][ld_out], channel = level * 81 + a * 9 + b where a
+ * offsets x and b offsets y (the reference's meshgrid order); channels [324, ld_out) are zeroed. */
+uav_status_t uav_raft_corr_lookup(const float* const* levels, const int32_t* hs, const int32_t* ws, const float* coords,
+                                  int64_t pixels, void* out, int64_t ld_out, uav_stream_t stream);
+/* SepConvGRU gate arithmetic (update.py:47-60), zr = [sigmoid(convz) | sigmoid(convr)] fp16 [rows][ld_zr]:
+ *   uav_raft_gru_rh:     out[:, :C] = r * h
+ *   uav_raft_gru_update: h = (1 - z) * h + z * q   (in place) */
+uav_status_t uav_raft_gru_rh(const void* zr, int64_t ld_zr, const void* h, int64_t ld_h, void* out, int64_t ld_out, int64_t rows,
+                             int64_t C, uav_stream_t stream);
+uav_status_t uav_raft_gru_update(const void* zr, int64_t ld_zr, const void* q, int64_t ld_q, void* h, int64_t ld_h, int64_t rows,
+                                 int64_t C, uav_stream_t stream);
+/* coords1 += delta (delta may be NULL), flow = coords1 - coords0 (raft.py:128-134) written as fp16 into channels [0, 2)
+ * of up to three [rows][ld] buffers (NULL = skip); rows = images * h8 * w8 */
+uav_status_t uav_raft_flow_update(float* coords1, const float* delta, int64_t ld_delta, int64_t rows, int64_t h8, int64_t w8,
+                                  void* flow16, int64_t ld16, void* dst_a, int64_t ld_a, void* dst_b, int64_t ld_b,
+                                  uav_stream_t stream);
+/* RAFT.upsample_flow (raft.py:73-84): mask fp16 [images*h8*w8][ld_mask] (576 channels = 9 x 8 x 8), out fp32 planar
+ * [images][2][8*h8][8*w8] */
+uav_status_t uav_raft_convex_upsample(const float* coords1, const void* mask, int64_t ld_mask, int64_t nimg, int64_t h8,
+                                      int64_t w8, float* out, uav_stream_t stream);
+
+/* ---- CLIP text encoder ---------------------------------------------------------------
+ * causal self-attention over a short sequence (transformers CLIPAttention under CLIPTextTransformer's causal mask):
+ * q, k, v, out fp16 [batch][n][ld] with `heads * head_dim` used columns (column slices of a fused qkv buffer allowed),
+ * n <= 128, head_dim <= 128 and even; out[i] = softmax_j<=i(scale * q_i . k_j) v_j */
+uav_status_t uav_attention_causal(const void* q, const void* k, const void* v, void* out, int64_t batch, int heads, int head_dim,
+                                  int64_t n, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale,
                                   uav_stream_t stream);
 
 #ifdef __cplusplus

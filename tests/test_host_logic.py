@@ -232,3 +232,13 @@ def test_upscale_tiled_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29519", str(script), ROOT],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "TILES_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_raft_state_dict_keys_match_reference():
+    """the RAFT parameter holders expose exactly the reference's state-dict keys and shapes (tests/golden/shapes_raft.json is
+    dumped from the reference model), so `raft-things.pth` loads with strict=True"""
+    import json
+    from upscale_a_video_b200.raft import RAFT
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "shapes_raft.json")))
+    sd = RAFT().state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == shapes

@@ -66,6 +66,17 @@ _PROTOS = {
     "uav_add_noise": [P, P, P, I64, F32, F32, I32, P],
     "uav_propagate_step": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I32, I32, F32, F32, F32,
                            I32, I32, P],
+    "uav_conv2d_taps": [P, I64, I64, I64, I64, I64, P, I64, I32, I32, I32, I32, P, EP, P],
+    "uav_instnorm_relu": [P, I64, I64, I64, F32, I32, P, P, P],
+    "uav_add_relu": [P, P, P, I64, P],
+    "uav_raft_split_tanh_relu": [P, I64, I64, P, I64, P, I64, P, I64, P],
+    "uav_avgpool2x2_f32": [P, I64, I64, I64, P, P],
+    "uav_raft_corr_lookup": [P, P, P, P, I64, P, I64, P],
+    "uav_raft_gru_rh": [P, I64, P, I64, P, I64, I64, I64, P],
+    "uav_raft_gru_update": [P, I64, P, I64, P, I64, I64, I64, P],
+    "uav_raft_flow_update": [P, P, I64, I64, I64, I64, P, I64, P, I64, P, I64, P],
+    "uav_raft_convex_upsample": [P, P, I64, I64, I64, I64, P, P],
+    "uav_attention_causal": [P, P, P, P, I64, I32, I32, I64, I64, I64, I64, I64, F32, P],
     "uav_bicubic_upsample": [P, I64, I64, I64, I32, P, P],
     "uav_plane_stats": [P, I64, I64, F32, P, P, P, P],
     "uav_adain_apply": [P, I64, I64, P, P, P, P, P, P],
@@ -78,6 +89,7 @@ _SPECIAL = {
     "uav_launch_count": (C.c_uint64, []),
     "uav_groupnorm_workspace_bytes": (C.c_size_t, [I64, I32]),
     "uav_plane_stats_workspace_bytes": (C.c_size_t, [I64]),
+    "uav_instnorm_workspace_bytes": (C.c_size_t, [I64, I64]),
 }
 
 

@@ -76,7 +76,7 @@ PFN_encodeTiled get_encode_tiled() {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // fp16 elements: one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int MAX_TAPS = 27;
+constexpr int MAX_TAPS = 49;  // up to 7 x 7 (RAFT motion encoder)
 constexpr int NUM_THREADS = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -134,6 +134,18 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+}
+// pointwise activations of the fused epilogue (GEGLU is handled separately: it pairs two accumulator columns)
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case UAV_ACT_SILU: return silu_f(x);
+    case UAV_ACT_RELU: return fmaxf(x, 0.f);
+    case UAV_ACT_SIGMOID: return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x));
+    case UAV_ACT_TANH: return 1.0f - 2.0f * rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x));
+    case UAV_ACT_GELU: return gelu_erf_f(x);
+    case UAV_ACT_QUICK_GELU: return x * rcp_ftz(1.0f + ex2_ftz(-2.4554669595930156f * x));  // x * sigmoid(1.702 x)
+    default: return x;
+  }
 }
 __device__ __forceinline__ void add_half8(float (&x)[8], const uint4& q) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&q);
@@ -476,9 +488,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j];
                 if constexpr (AUX) {
                   if (rv != nullptr) add_half8(x, vq[g]);
-                  if (p.act == UAV_ACT_SILU) {
+                  if (p.act != UAV_ACT_NONE) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+                    for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
                   }
                   if (res != nullptr) add_half8(x, rq[g]);
                 }
@@ -572,9 +584,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                   for (int j = 0; j < 8; ++j) x[j] = v[g8 * 8 + j];
                   if (rv != nullptr) add_half8(x, ldg16(rv + n));
-                  if (p.act == UAV_ACT_SILU) {
+                  if (p.act != UAV_ACT_NONE) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+                    for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
                   }
                   if (res != nullptr) add_half8(x, ldg16(res + n));
                   if (p.out_dtype == UAV_F16) {
@@ -598,7 +610,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 if (n < p.n_out) {
                   float x = v[j];
                   if (rv != nullptr) x += __half2float(rv[n]);
-                  if (p.act == UAV_ACT_SILU) x = silu_f(x);
+                  x = apply_act(x, p.act);
                   if (res != nullptr) x += __half2float(res[n]);
                   if (p.out_dtype == UAV_F16)
                     reinterpret_cast<__half*>(p.out)[out_row * p.ld_out + n] = __float2half_rn(x);
@@ -697,7 +709,7 @@ static uav_status_t launch_instance2(IgemmParams& p, bool cluster, cudaStream_t 
 
 template <int BLOCK_N, bool GEGLU>
 static uav_status_t launch_instance(IgemmParams& p, bool cluster, cudaStream_t stream) {
-  const bool aux = p.rowvec != nullptr || p.residual != nullptr || p.act == UAV_ACT_SILU;
+  const bool aux = p.rowvec != nullptr || p.residual != nullptr || (p.act != UAV_ACT_NONE && p.act != UAV_ACT_GEGLU);
   if constexpr (IgemmCfg<BLOCK_N, GEGLU>::OUT_TILE_N >= 64) {
     if (p.tma_store) {
       return aux ? launch_instance2<BLOCK_N, GEGLU, true, true>(p, cluster, stream)
@@ -834,8 +846,7 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   UAV_REQUIRE(p.ld_out >= p.n_out, "igemm: ld_out (%lld) < output columns (%d)",
               (long long)p.ld_out, p.n_out);
   UAV_REQUIRE(e->out_dtype == UAV_F16 || e->out_dtype == UAV_F32, "igemm: bad out_dtype");
-  UAV_REQUIRE(e->act == UAV_ACT_NONE || e->act == UAV_ACT_SILU || e->act == UAV_ACT_GEGLU,
-              "igemm: bad activation");
+  UAV_REQUIRE(e->act >= UAV_ACT_NONE && e->act <= UAV_ACT_QUICK_GELU, "igemm: bad activation");
   if (p.num_tiles == 0) return UAV_OK;
 
   // TMA-store epilogue (smem-staged, fully coalesced, clips partial tiles) whenever the output
@@ -1015,6 +1026,49 @@ uav_status_t uav_conv2d(const void* x, int64_t NB, int64_t H, int64_t W, int64_t
         o[4] = 0;
       }
   }
+  return launch_igemm(d, (cudaStream_t)stream);
+}
+
+uav_status_t uav_conv2d_taps(const void* x, int64_t NB, int64_t H, int64_t W, int64_t Cin, int64_t ld_in,
+                             const void* w, int64_t Cout, int kh, int kw, int pad_top, int pad_left, void* out,
+                             const uav_epilogue_t* epi, uav_stream_t stream) {
+  UAV_REQUIRE(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && ld_in >= Cin, "uav_conv2d_taps: bad shape");
+  UAV_REQUIRE(kh >= 1 && kw >= 1 && kh * kw <= MAX_TAPS, "uav_conv2d_taps: at most %d taps (got %d x %d)", MAX_TAPS, kh,
+              kw);
+  UAV_REQUIRE(pad_top >= 0 && pad_top < kh && pad_left >= 0 && pad_left < kw, "uav_conv2d_taps: bad padding");
+  IgemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.a = x;
+  d.w = w;
+  d.N = Cout;
+  d.out = out;
+  d.epi = epi;
+  d.k_per_tap = (int)Cin;
+  uint32_t tw, th;
+  pick_tile_2d(W, H, &tw, &th);
+  const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 1};
+  const uint64_t strides[5] = {1, (uint64_t)ld_in, (uint64_t)ld_in * W, (uint64_t)ld_in * W * H,
+                               (uint64_t)ld_in * W * H * NB};
+  const uint32_t box[5] = {64, tw, th, 1, 1};
+  const uint32_t tiles[5] = {1, (uint32_t)((W + tw - 1) / tw), (uint32_t)((H + th - 1) / th), (uint32_t)NB, 1};
+  const uint32_t odims[5] = {1, (uint32_t)W, (uint32_t)H, (uint32_t)NB, 1};
+  for (int i = 0; i < 5; ++i) {
+    d.a_dims[i] = dims[i];
+    d.a_strides[i] = strides[i];
+    d.box[i] = box[i];
+    d.tiles[i] = tiles[i];
+    d.out_dims[i] = odims[i];
+  }
+  d.num_taps = kh * kw;
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      int32_t* o = d.tap_off[ky * kw + kx];
+      o[0] = 0;
+      o[1] = kx - pad_left;
+      o[2] = ky - pad_top;
+      o[3] = 0;
+      o[4] = 0;
+    }
   return launch_igemm(d, (cudaStream_t)stream);
 }
 

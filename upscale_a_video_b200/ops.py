@@ -564,3 +564,142 @@ def pack_video_uint8(frames: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _lib.check(lib.uav_pack_video_uint8(frames.data_ptr(), t, c, h, w, out.data_ptr(), _stream()), "uav_pack_video_uint8")
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# RAFT optical flow (csrc/raft.cu + uav_conv2d_taps): channels-last fp16 activations, fp32 correlation / coordinates
+# ---------------------------------------------------------------------------------------
+ACT_RELU, ACT_SIGMOID, ACT_TANH = 3, 4, 5
+
+
+def conv2d_taps(x: torch.Tensor, w: torch.Tensor, bias=None, *, pad_top: int, pad_left: int, out=None, residual=None,
+                act=ACT_NONE, out_dtype=torch.float16):
+    """stride-1 same-size conv with a (kh, kw) window and asymmetric padding; x (N, H, W, Cin) fp16 (channel-slice views
+    allowed), w (Cout, kh, kw, Cin) fp16"""
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous() and x.dim() == 4
+    NB, H, W, Cin = x.shape
+    Cout, kh, kw, Cin_w = w.shape
+    assert Cin_w == Cin, (Cin_w, Cin)
+    if out is None:
+        out = torch.empty(NB, H, W, Cout, dtype=out_dtype, device=x.device)
+    assert tuple(out.shape) == (NB, H, W, Cout)
+    e = _epi(out, bias, None, 0, residual, act)
+    lib = _lib.load()
+    with _timed("igemm", 2.0 * NB * H * W * Cout * Cin * kh * kw,
+                2.0 * (NB * H * W * Cin + w.numel()) + out.element_size() * NB * H * W * Cout,
+                f"conv{kh}x{kw}taps {NB}x{H}x{W} {Cin}->{Cout}"):
+        _lib.check(lib.uav_conv2d_taps(x.data_ptr(), NB, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout, kh, kw, pad_top,
+                                       pad_left, out.data_ptr(), C.byref(e), _stream()), "uav_conv2d_taps")
+    return out
+
+
+def instnorm_relu(x: torch.Tensor, relu: bool = True, eps: float = 1e-5) -> torch.Tensor:
+    """(N, H, W, C) fp16 contiguous -> InstanceNorm2d (no affine) (+ ReLU)"""
+    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 4
+    n, h, w, c = x.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.uav_instnorm_workspace_bytes(n, c), dtype=torch.uint8, device=x.device)
+    y = torch.empty_like(x)
+    _lib.check(lib.uav_instnorm_relu(x.data_ptr(), n, h * w, c, eps, 1 if relu else 0, y.data_ptr(), ws.data_ptr(), _stream()),
+               "uav_instnorm_relu")
+    return y
+
+
+def add_relu(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    assert a.shape == b.shape and a.dtype == b.dtype == torch.float16 and a.is_contiguous() and b.is_contiguous()
+    y = torch.empty_like(a)
+    lib = _lib.load()
+    _lib.check(lib.uav_add_relu(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream()), "uav_add_relu")
+    return y
+
+
+def raft_split_tanh_relu(cnet: torch.Tensor, net: torch.Tensor, inp_a: torch.Tensor, inp_b: Optional[torch.Tensor]):
+    """cnet (rows, 2C) fp16 contiguous; net / inp_* are (rows, C) channel-slice views"""
+    rows, c2 = cnet.shape
+    lib = _lib.load()
+    _lib.check(lib.uav_raft_split_tanh_relu(cnet.data_ptr(), rows, c2 // 2, net.data_ptr(), net.stride(0), inp_a.data_ptr(),
+                                            inp_a.stride(0), inp_b.data_ptr() if inp_b is not None else None,
+                                            inp_b.stride(0) if inp_b is not None else 0, _stream()), "uav_raft_split_tanh_relu")
+
+
+def avgpool2x2_f32(x: torch.Tensor) -> torch.Tensor:
+    """(planes, h, w) fp32 -> (planes, h // 2, w // 2)"""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    planes, h, w = x.shape
+    out = torch.empty(planes, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_avgpool2x2_f32(x.data_ptr(), planes, h, w, out.data_ptr(), _stream()), "uav_avgpool2x2_f32")
+    return out
+
+
+def raft_corr_lookup(levels, coords: torch.Tensor, out: torch.Tensor):
+    """levels: 4 fp32 tensors (pixels, h_i, w_i); coords (pixels, 2) fp32; out (pixels, >= 324) fp16 contiguous"""
+    assert len(levels) == 4 and coords.dtype == torch.float32 and coords.is_contiguous() and out.dtype == torch.float16
+    pixels = coords.shape[0]
+    ptrs = (C.c_void_p * 4)(*[lv.data_ptr() for lv in levels])
+    hs = (C.c_int32 * 4)(*[lv.shape[1] for lv in levels])
+    ws = (C.c_int32 * 4)(*[lv.shape[2] for lv in levels])
+    for lv in levels:
+        assert lv.dtype == torch.float32 and lv.is_contiguous() and lv.shape[0] == pixels
+    lib = _lib.load()
+    _lib.check(lib.uav_raft_corr_lookup(ptrs, hs, ws, coords.data_ptr(), pixels, out.data_ptr(), out.stride(0), _stream()),
+               "uav_raft_corr_lookup")
+    return out
+
+
+def raft_gru_rh(zr: torch.Tensor, h: torch.Tensor, out: torch.Tensor):
+    rows, c = h.shape
+    lib = _lib.load()
+    _lib.check(lib.uav_raft_gru_rh(zr.data_ptr(), zr.stride(0), h.data_ptr(), h.stride(0), out.data_ptr(), out.stride(0), rows, c,
+                                   _stream()), "uav_raft_gru_rh")
+
+
+def raft_gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor):
+    rows, c = h.shape
+    lib = _lib.load()
+    _lib.check(lib.uav_raft_gru_update(zr.data_ptr(), zr.stride(0), q.data_ptr(), q.stride(0), h.data_ptr(), h.stride(0), rows, c,
+                                       _stream()), "uav_raft_gru_update")
+
+
+def raft_flow_update(coords1: torch.Tensor, delta: Optional[torch.Tensor], h8: int, w8: int, flow16=None, dst_a=None, dst_b=None):
+    """coords1 (rows, 2) fp32 in place (+= delta (rows, >= 2) fp32); fp16 flow into channels [0, 2) of the given views"""
+    rows = coords1.shape[0]
+    lib = _lib.load()
+
+    def pl(t):
+        return (t.data_ptr(), t.stride(0)) if t is not None else (None, 0)
+
+    _lib.check(lib.uav_raft_flow_update(coords1.data_ptr(), delta.data_ptr() if delta is not None else None,
+                                        delta.stride(0) if delta is not None else 0, rows, h8, w8, *pl(flow16), *pl(dst_a),
+                                        *pl(dst_b), _stream()), "uav_raft_flow_update")
+
+
+def raft_convex_upsample(coords1: torch.Tensor, mask: torch.Tensor, nimg: int, h8: int, w8: int) -> torch.Tensor:
+    out = torch.empty(nimg, 2, 8 * h8, 8 * w8, dtype=torch.float32, device=coords1.device)
+    lib = _lib.load()
+    _lib.check(lib.uav_raft_convex_upsample(coords1.data_ptr(), mask.data_ptr(), mask.stride(0), nimg, h8, w8, out.data_ptr(),
+                                            _stream()), "uav_raft_convex_upsample")
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# CLIP text encoder: causal attention over the 77-token prompt, GELU epilogues
+# ---------------------------------------------------------------------------------------
+ACT_GELU, ACT_QUICK_GELU = 6, 7
+
+
+def attention_causal(q, k, v, heads: int, *, scale: Optional[float] = None, out=None):
+    """q, k, v: (batch, n, heads*d) fp16 (column slices of a fused qkv buffer allowed), n <= 128"""
+    batch, n, Cc = q.shape
+    d = Cc // heads
+    if out is None:
+        out = torch.empty(batch, n, Cc, dtype=torch.float16, device=q.device)
+    if scale is None:
+        scale = d ** -0.5
+    for t in (q, k, v, out):
+        assert t.is_cuda and t.dtype == torch.float16 and t.stride(-1) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    lib = _lib.load()
+    _lib.check(lib.uav_attention_causal(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, d, n,
+                                        q.stride(1), k.stride(1), v.stride(1), out.stride(1), scale, _stream()),
+               "uav_attention_causal")
+    return out
