@@ -6,12 +6,18 @@
 
 One "step" = one full pass of the hot path over one synthetic clip: `VideoUpscalePipeline.__call__` with 30 DDIM
 steps (chunked UNet, CFG, step_v0, flow propagation at steps 24/26/28, step_vt) followed by the chunked VAE decode.
-N=1 runs BASELINE.json configs[1]: 8 frames 320x576 -> 1280x2304, guidance 6, fp16.  N>1 is weak scaling: the clip
+N=1 runs BASELINE.json configs[1] ("c2"): 8 frames 320x576 -> 1280x2304, guidance 6, fp16.  N>1 is weak scaling: the clip
 has 8 + 6*(N-1) frames, i.e. exactly N unique 8-frame UNet windows per DDIM step (one per rank) and ceil(T/3) decode
 chunks dealt over ranks; one NCCL all_gather per DDIM step + one at the end (upscale_a_video_b200/sharding.py).
+`--config c3|c4|c5|clip64` (hidden; recorded into profiles/ by hand) select the other BASELINE configs.
 
 `value`: frames/s with inputs resident in HBM, CUDA-event timed, max over ranks.  `e2e`: same through the public API
 with pinned HOST buffers (H2D of the LR clip + flows, D2H of the decoded frames inside the timed region).
+`reference_gpu` (N=1): the reference's own op sequence (oracle restatement = the same torch / cuDNN / cuBLAS calls) in the
+reference's precision mode (fp16 UNet + sampler, fp32 VAE) on the same GPU, same clip, same timing window
+(inference_upscale_a_video.py:205-206,335-338) — north_star's ">= 4x the reference's single-B200 fp16 path" denominator.
+`cpu_baseline` / `--impl reference`: the oracle on the host cores, on a bounded sample (UNet forward + VAE decode chunk +
+sampler step at reduced size), each part scaled to config 2 by its algorithmic FLOPs.
 Weights are random-init (no checkpoints offline), inputs synthetic (seeded) — see `data`.
 """
 import argparse
@@ -29,9 +35,19 @@ import torch  # noqa: E402
 
 # algorithmic work
 UNET_TFLOP_PER_FWD_C2 = 319.96     # B=2, T=8, 320x576
-VAE_TFLOP_PER_3F_C2 = 294.6        # 3-frame chunk, 320x576, vae_3d
-H_LR, W_LR, STEPS_DDIM, GUIDANCE, NOISE_LEVEL = 320, 576, 30, 6.0, 120
-PROP_STEPS = [24, 26, 28]
+VAE_CONV_TFLOP_PER_3F_C2 = 85.6    # 3-frame chunk, 320x576, vae_3d: convolutions + projections
+VAE_ATTN_TFLOP_PER_3F_C2 = 209.0   # ... single-head d=512 attention over 184 320 positions
+VAE_TFLOP_PER_3F_C2 = VAE_CONV_TFLOP_PER_3F_C2 + VAE_ATTN_TFLOP_PER_3F_C2
+GUIDANCE, NOISE_LEVEL = 6.0, 120
+
+# BASELINE.json configs.  `frames=None`: weak scaling, 8 + 6 (N - 1) frames.
+CONFIGS = {
+    "c2": dict(frames=None, h=320, w=576, steps=30, prop=[24, 26, 28], vae="vae_3d", tiled=False),
+    "c3": dict(frames=32, h=320, w=576, steps=30, prop=[24, 26, 28], vae="vae_3d", tiled=False),
+    "c4": dict(frames=64, h=180, w=320, steps=30, prop=[24, 26, 28], vae="vae_video", tiled=False),
+    "c5": dict(frames=16, h=540, w=960, steps=50, prop=[40, 44, 48], vae="vae_3d", tiled=True),
+    "clip64": dict(frames=64, h=320, w=576, steps=30, prop=[24, 26, 28], vae="vae_3d", tiled=False),
+}
 
 
 def frames_for(n_gpus):
@@ -51,9 +67,16 @@ def synth_inputs(T, H, W, device):
     return image, fw, bw, pe
 
 
-def seeded_state_dict(module, seed):
-    from oracle.weights import make_state_dict  # deterministic random init (no checkpoints exist offline)
-    return make_state_dict({k: tuple(v.shape) for k, v in module.state_dict().items()}, seed)
+def _shapes(kind):
+    return json.load(open(os.path.join(ROOT, "tests", "golden", f"shapes_{kind}.json")))
+
+
+def _cfg(kind):
+    return json.load(open(os.path.join(ROOT, "upscale_a_video_b200", "configs", f"{kind}_config.json")))
+
+
+SCHED = dict(beta_schedule="scaled_linear", clip_sample=False, steps_offset=1, prediction_type="v_prediction",
+             set_alpha_to_one=False)  # SD-x4-upscaler style
 
 
 class ClockSampler:
@@ -90,86 +113,224 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_pipeline(device):
+def build_pipeline(device, vae_kind="vae_3d"):
     from upscale_a_video_b200 import (AutoencoderKLVideo, DDIMScheduler, DDPMScheduler, Propagation, UNetVideoModel,
                                       VideoUpscalePipeline)
-    cfgdir = os.path.join(ROOT, "upscale_a_video_b200", "configs")
-    unet = UNetVideoModel.from_config(json.load(open(os.path.join(cfgdir, "unet_video_config.json"))))
+    from upscale_a_video_b200.synthetic import seeded_state_dict  # deterministic random init (no checkpoints offline)
+    unet = UNetVideoModel.from_config(_cfg("unet_video"))
     unet.load_state_dict(seeded_state_dict(unet, 1234), strict=True)
     unet = unet.half().eval().to(device)
-    vae = AutoencoderKLVideo.from_config(json.load(open(os.path.join(cfgdir, "vae_3d_config.json"))))
+    vae = AutoencoderKLVideo.from_config(_cfg(vae_kind))
     vae.load_state_dict(seeded_state_dict(vae, 4321), strict=True)
     vae = vae.eval().to(device)
-    sched = DDIMScheduler(beta_schedule="scaled_linear", clip_sample=False, steps_offset=1, prediction_type="v_prediction",
-                          set_alpha_to_one=False)  # SD-x4-upscaler style
     return VideoUpscalePipeline(text_encoder=None, tokenizer=None, low_res_scheduler=DDPMScheduler(beta_schedule="scaled_linear"),
-                                scheduler=sched, vae=vae, unet=unet, propagator=Propagation(4, learnable=False))
+                                scheduler=DDIMScheduler(**SCHED), vae=vae, unet=unet, propagator=Propagation(4, learnable=False))
 
 
-_CPU_SD = None
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (CPU port of the reference path) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+# (T, H, W) of the oracle UNet forward (B=2) and (H, W) of the 3-frame VAE decode chunk, smallest to largest
+_UNET_SIZES = [(1, 16, 16), (1, 32, 32), (2, 32, 32), (2, 48, 48), (2, 64, 64), (4, 64, 64), (4, 64, 96), (4, 96, 128)]
+_VAE_SIZES = [(8, 8), (16, 16), (24, 24), (32, 32), (48, 48), (64, 64)]
 
 
-def cpu_baseline_sample(threads=None):
-    """the oracle (CPU port of the reference path) on a bounded sample, scaled by algorithmic FLOPs"""
+def _unet_tflop(T, H, W):
+    # UNet work scales ~linearly in T*H*W away from the (small) self-attention term
+    return UNET_TFLOP_PER_FWD_C2 * (T * H * W) / (8 * 320 * 576)
+
+
+def _vae_tflop(H, W):
+    r = (H * W) / (320 * 576)
+    return VAE_CONV_TFLOP_PER_3F_C2 * r + VAE_ATTN_TFLOP_PER_3F_C2 * r * r
+
+
+def _cpu_state():
+    if not _CPU:
+        from oracle.weights import make_state_dict
+        _CPU["usd"] = make_state_dict(_shapes("unet"), 1234)
+        _CPU["vsd"] = make_state_dict(_shapes("vae_3d"), 4321)
+        _CPU["ucfg"], _CPU["vcfg"] = _cfg("unet_video"), _cfg("vae_3d")
+        torch.set_num_threads(os.cpu_count() or 1)   # all host cores, stated in `cores`
+    return _CPU
+
+
+def _cpu_unet(T, H, W):
     from oracle import uav_oracle as O
-    from oracle.weights import make_state_dict
-    # torch's CPU kernels do not scale to every core of a 100+-core host on these small tensors: pick the fastest of a
-    # few thread counts on a tiny warm-up forward, and report the count actually used as `cores`
-    best = (None, float("inf"))
-    cfgdir = os.path.join(ROOT, "upscale_a_video_b200", "configs")
-    ucfg = json.load(open(os.path.join(cfgdir, "unet_video_config.json")))
-    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "shapes_unet.json")))
-    global _CPU_SD
-    if _CPU_SD is None:
-        _CPU_SD = make_state_dict(shapes, 1234)
-    sd = _CPU_SD
-    B, T, H, W = 2, 4, 96, 128  # bounded sample: ~10-20 s on 16-32 host threads
+    st = _cpu_state()
     g = torch.Generator().manual_seed(0)
-    sample, low = torch.randn(B, 4, T, H, W, generator=g), torch.randn(B, 3, T, H, W, generator=g)
-    ctx = torch.randn(B, 77, 1024, generator=g) * 0.3
+    sample, low = torch.randn(2, 4, T, H, W, generator=g), torch.randn(2, 3, T, H, W, generator=g)
+    ctx = torch.randn(2, 77, 1024, generator=g) * 0.3
+    t0 = time.time()
     with torch.no_grad():
-        cands = [threads] if threads else sorted({min(os.cpu_count(), c) for c in (8, 16, 32, 64, os.cpu_count())})
-        for nt in cands:
-            torch.set_num_threads(nt)
-            t0 = time.time()
-            O.unet_forward(sd, ucfg, sample[:, :, :1, :16, :16], torch.tensor(500), low[:, :, :1, :16, :16], ctx, torch.tensor([120]))
-            dt = time.time() - t0
-            if dt < best[1]:
-                best = (nt, dt)
-        torch.set_num_threads(best[0])
-        t0 = time.time()
-        O.unet_forward(sd, ucfg, sample, torch.tensor(500), low, ctx, torch.tensor([120]))
-        dt = time.time() - t0
-    # UNet work scales ~linearly in T*H*W away from the self-attention term (SURVEY.md §8d)
-    tflop = UNET_TFLOP_PER_FWD_C2 * (T * H * W) / (8 * H_LR * W_LR)
-    cpu_tflops = tflop / dt
-    per_frame_tflop = STEPS_DDIM * UNET_TFLOP_PER_FWD_C2 / 8 + VAE_TFLOP_PER_3F_C2 / 3
-    return {"value": cpu_tflops / per_frame_tflop, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle UNet forward B=2,T={T},{H}x{W} fp32 ({tflop:.2f} TFLOP algorithmic) in {dt:.1f} s = "
-                      f"{cpu_tflops:.3f} TFLOP/s, scaled by algorithmic FLOPs/frame ({per_frame_tflop:.0f} TFLOP) to config 2"}
+        O.unet_forward(st["usd"], st["ucfg"], sample, torch.tensor(500), low, ctx, torch.tensor([120]))
+    return time.time() - t0
+
+
+def _cpu_vae(H, W):
+    from oracle import uav_oracle as O
+    st = _cpu_state()
+    g = torch.Generator().manual_seed(0)
+    z, img = torch.randn(1, 4, 3, H, W, generator=g), torch.rand(1, 3, 3, H, W, generator=g)
+    t0 = time.time()
+    with torch.no_grad():
+        O.vae_decode(st["vsd"], st["vcfg"], z, img, 1.0)
+    return time.time() - t0
+
+
+def _cpu_sampler(T, H, W):
+    """CFG + step_v0 + propagation + step_vt of one DDIM step on a (1,4,T,H,W) latent (oracle, fp32)"""
+    from oracle import uav_oracle as O
+    g = torch.Generator().manual_seed(0)
+    lat, pred2 = torch.randn(1, 4, T, H, W, generator=g), torch.randn(2, 4, T, H, W, generator=g)
+    fw, bw = torch.randn(1, 2, T - 1, H, W, generator=g), torch.randn(1, 2, T - 1, H, W, generator=g)
+    s = O.DDIM(**SCHED)
+    s.set_timesteps(30)
+    t0 = time.time()
+    with torch.no_grad():
+        u, c = pred2.chunk(2)
+        p = u + GUIDANCE * (c - u)
+        x0 = s.step_v0(p, s.timesteps[3], lat)
+        x0 = O.propagation(x0, fw, bw, "nearest", "fuse", 0.5, 0.001, 0.05)
+        s.step_vt(x0, p, s.timesteps[3], lat)
+    return time.time() - t0
+
+
+def cpu_plan(target_s):
+    """pick the largest sample sizes whose predicted time fits `target_s` (calibrated on the smallest size)"""
+    _cpu_state()
+    _cpu_unet(*_UNET_SIZES[0])  # warm-up (thread pool, allocator)
+    tu = _cpu_unet(*_UNET_SIZES[0]) / _unet_tflop(*_UNET_SIZES[0])   # s / TFLOP
+    tv = _cpu_vae(*_VAE_SIZES[0]) / _vae_tflop(*_VAE_SIZES[0])
+    us = _UNET_SIZES[0]
+    for s in _UNET_SIZES:   # small tensors under-use the cores, so the calibration over-predicts: conservative
+        if _unet_tflop(*s) * tu <= 0.75 * target_s:
+            us = s
+    vs = _VAE_SIZES[0]
+    for s in _VAE_SIZES:
+        if _vae_tflop(*s) * tv <= 0.25 * target_s:
+            vs = s
+    return us, vs
+
+
+def cpu_sample(plan):
+    """one bounded sample; each part scaled separately by its algorithmic FLOPs to one config-2 frame"""
+    (T, H, W), (hv, wv) = plan
+    tu, tv, ts = _cpu_unet(T, H, W), _cpu_vae(hv, wv), _cpu_sampler(8, 64, 64)
+    wu, wv_ = _unet_tflop(T, H, W), _vae_tflop(hv, wv)
+    per_frame_s = (tu * (30 * UNET_TFLOP_PER_FWD_C2 / 8) / wu      # 30 UNet forwards per 8 frames
+                   + tv * (VAE_TFLOP_PER_3F_C2 / 3) / wv_           # decode, per frame
+                   + ts * 3 * (320 * 576) / (64 * 64) / 8)          # 3 propagation steps per clip, per frame (+ cheap rest)
+    return {"value": 1.0 / per_frame_s, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "seconds": tu + tv + ts,
+            "sample": f"oracle (fp32, {torch.get_num_threads()} threads): UNet forward B=2,T={T},{H}x{W} ({wu:.2f} TFLOP) in {tu:.1f} s"
+                      f" + vae_3d decode 3x{hv}x{wv} ({wv_:.3f} TFLOP) in {tv:.1f} s + one sampler step 8x64x64 in {ts:.2f} s;"
+                      f" each part scaled by its algorithmic FLOPs to config 2 ({30 * UNET_TFLOP_PER_FWD_C2 / 8:.0f} + "
+                      f"{VAE_TFLOP_PER_3F_C2 / 3:.0f} TFLOP per frame)"}
 
 
 def run_reference_arm(args):
-    """the reference's own CPU implementation of the path (oracle port; /root/reference does not exist on the GPU box)"""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """the reference's own CPU implementation of the path (oracle port; /root/reference does not exist on the GPU box).
+    Each step is ONE bounded sample, sized once so that warmup + steps samples take ~2.5 minutes in total."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    vals = []
-    cb = None
-    for i in range(args.warmup + args.steps):
-        cb = cpu_baseline_sample()
+    n = args.warmup + args.steps
+    plan = cpu_plan(max(1.0, 150.0 / max(n, 1)))
+    vals, secs, cb = [], [], None
+    for i in range(n):
+        cb = cpu_sample(plan)
         if i >= args.warmup:
             vals.append(cb["value"])
+            secs.append(cb["seconds"])
     v = sum(vals) / len(vals)
     cb["value"] = v
     T = frames_for(args.gpus)
+    ms = 1000.0 * sum(secs) / len(secs)
     _emit({"impl": "reference", "metric": "upscaled frames/sec (30 DDIM steps, 320x576->4x)", "value": v,
-                      "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": 1000.0 * T / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                      "dtype": "f32", "data": "synthetic, random-init weights",
-                      "config": {"workload": f"{T}-frame 320x576->1280x2304, 30 DDIM steps, guidance 6 (CPU: bounded sample, FLOP-scaled)"},
-                      "cpu_baseline": cb,
-                      "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+           "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms, "frames_equivalent_per_step": v * ms / 1000.0,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic, random-init weights",
+           "config": {"workload": f"{T}-frame 320x576->1280x2304, 30 DDIM steps, guidance 6 — CPU: each step is one bounded "
+                                  "sample (UNet forward + VAE decode chunk + sampler step at reduced size), FLOP-scaled per part; "
+                                  "value = frames_equivalent_per_step / (ms_per_step / 1000)"},
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+# ------------------------------------------------------------------------------------------------
+# reference on the same GPU (north_star's >= 4x denominator)
+# ------------------------------------------------------------------------------------------------
+def reference_gpu_leg(device, h_image, h_fw, h_bw, pe, steps, prop):
+    """the reference's op sequence (oracle restatement: the same torch ops the reference modules call -> cuDNN / cuBLAS
+    kernels) in the reference's precision mode: UNet + sampler fp16 (`.half()`), VAE fp32 (pipeline...:668-669) with torch's
+    default TF32 convolutions; cudnn.benchmark on; the N = 184 320 VAE attention through the faster of torch's fused SDPA and
+    an exact row-blocked softmax (the reference's dense score matrix is 136 GB per frame and cannot run).  ONE full clip,
+    timed like inference_upscale_a_video.py:205-206,335-338 (synchronize, pipeline call, output.cpu(), synchronize).
+    Favourable to the reference: no per-step empty_cache() / .item() syncs (the reference has both)."""
+    from oracle import uav_oracle as O
+    from oracle.weights import make_state_dict
+    bench_flag = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        usd = {k: v.to(device).half() for k, v in make_state_dict(_shapes("unet"), 1234).items()}
+        vsd = {k: v.to(device) for k, v in make_state_dict(_shapes("vae_3d"), 4321).items()}
+        ucfg, vcfg = _cfg("unet_video"), _cfg("vae_3d")
+        T, H, W = h_image.shape[2:]
+        pe16 = pe.to(device).half()
+
+        def sync():
+            torch.cuda.synchronize(device)
+
+        with torch.no_grad():
+            # warm-up: cuDNN autotuning of every conv shape (UNet forward, one decode chunk per attention variant)
+            lat = torch.randn(2, 4, T, H, W, device=device, dtype=torch.float16)
+            low = torch.randn(2, 3, T, H, W, device=device, dtype=torch.float16)
+            O.unet_forward(usd, ucfg, lat, torch.tensor(500), low, pe16, torch.tensor([NOISE_LEVEL]))
+            z = torch.randn(1, 4, 3, H, W, device=device)
+            img = torch.rand(1, 3, 3, H, W, device=device)
+            impl_ms = {}
+            for impl in ("exact", "sdpa"):
+                O.ATTN_LARGE_IMPL = impl
+                try:
+                    O.vae_decode(vsd, vcfg, z, img, 1.0)
+                    sync()
+                    t0 = time.time()
+                    O.vae_decode(vsd, vcfg, z, img, 1.0)
+                    sync()
+                    impl_ms[impl] = 1000.0 * (time.time() - t0)
+                except Exception as ex:  # e.g. no fused kernel for head_dim 512 fp32 -> math fallback OOM
+                    impl_ms[impl] = None
+                    torch.cuda.empty_cache()
+                    print(f"[reference_gpu] VAE attention impl {impl} unavailable: {type(ex).__name__}", file=sys.stderr)
+            ok = {k: v for k, v in impl_ms.items() if v is not None}
+            O.ATTN_LARGE_IMPL = min(ok, key=ok.get)
+            del lat, low, z, img
+            torch.cuda.empty_cache()
+            sync()
+            t0 = time.time()
+            gen = torch.Generator(device=device).manual_seed(10)
+            image = h_image.to(device, non_blocking=True)
+            flows = [h_fw.to(device, non_blocking=True), h_bw.to(device, non_blocking=True)]
+            noise = torch.randn(image.shape, generator=gen, device=device, dtype=torch.float16)
+            lat0 = torch.randn(1, 4, T, H, W, generator=gen, device=device, dtype=torch.float16)
+            out = O.pipeline_call(usd, ucfg, vsd, vcfg, O.DDIM(**SCHED), O.DDIM(beta_schedule="scaled_linear"), image=image,
+                                  prompt_embeds=pe16, noise=noise, latents=lat0, flows_bi=flows, num_inference_steps=steps,
+                                  guidance_scale=GUIDANCE, noise_level=NOISE_LEVEL, propagation_steps=prop)
+            out_h = out.cpu()
+            sync()
+            dt = time.time() - t0
+            impl = O.ATTN_LARGE_IMPL
+            O.ATTN_LARGE_IMPL = "exact"
+        return {"value": T / dt, "unit": "frames/s", "seconds_per_clip": dt, "clips_timed": 1, "frames": int(T),
+                "kind": "reference op sequence (oracle restatement, torch -> cuDNN/cuBLAS) on the same GPU",
+                "precision": "UNet + sampler fp16, VAE fp32 (TF32 convolutions: torch default), cudnn.benchmark",
+                "vae_attention": impl, "vae_decode_chunk_ms": impl_ms,
+                "window": "synchronize; H2D inputs; pipeline call; output.cpu(); synchronize (inference_upscale_a_video.py:205-206,335-338)",
+                "output_checksum": float(out_h.double().abs().mean())}
+    finally:
+        torch.backends.cudnn.benchmark = bench_flag
 
 
 _REAL_STDOUT = None
@@ -190,21 +351,36 @@ def _emit(line: dict):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def _ncu_profile_of_dominant_kernel():
+    """DRAM traffic / tensor-pipe numbers of the representative igemm launch from the committed `ncu --set full` summary
+    (profiles/ncu_igemm_representative.json, written by tools/summarize_ncu.py from a capture of the same launch)."""
+    p = os.path.join(ROOT, "profiles", "ncu_igemm_representative.json")
+    try:
+        d = json.load(open(p))
+        d["source"] = "profiles/ncu_igemm_representative.json"
+        return d
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="uav_b200")
-    ap.add_argument("--ddim-steps", type=int, default=STEPS_DDIM, help=argparse.SUPPRESS)  # debugging only
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help=argparse.SUPPRESS)
+    ap.add_argument("--ddim-steps", type=int, default=0, help=argparse.SUPPRESS)  # debugging only
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-reference-gpu", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-e2e", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch.distributed as dist
-    from upscale_a_video_b200 import _lib, build, ops
+    from upscale_a_video_b200 import _lib, build, ops, sharding
     build.build()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -216,25 +392,35 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    T = frames_for(args.gpus)
-    pipe = build_pipeline(device)
+    cfg = CONFIGS[args.config]
+    T = cfg["frames"] or frames_for(args.gpus)
+    H_LR, W_LR = cfg["h"], cfg["w"]
+    ddim_steps = args.ddim_steps or cfg["steps"]
+    pipe = build_pipeline(device, cfg["vae"])
     image, fw, bw, pe = synth_inputs(T, H_LR, W_LR, device)
     neg, pos = pe.half().to(device).chunk(2)
-    kw = dict(num_inference_steps=args.ddim_steps, guidance_scale=GUIDANCE, noise_level=NOISE_LEVEL,
-              propagation_steps=[s for s in PROP_STEPS if s < args.ddim_steps], prompt_embeds=pos, negative_prompt_embeds=neg)
+    prop = [s for s in cfg["prop"] if s < ddim_steps]
+    kw = dict(num_inference_steps=ddim_steps, guidance_scale=GUIDANCE, noise_level=NOISE_LEVEL, propagation_steps=prop,
+              prompt_embeds=pos, negative_prompt_embeds=neg)
     d_image, d_fw, d_bw = image.to(device), fw.to(device), bw.to(device)
     h_image, h_fw, h_bw = image.pin_memory(), fw.pin_memory(), bw.pin_memory()
     h_out = torch.empty(1, 3, T, 4 * H_LR, 4 * W_LR, dtype=torch.float32).pin_memory()
 
+    def run_pipe(img, flows, gen):
+        if cfg["tiled"]:
+            from upscale_a_video_b200.tiling import upscale_tiled   # inference_upscale_a_video.py:200-304
+            return upscale_tiled(pipe, img, flows, generator=gen, tile_size=256, overlap=64, **kw)
+        return pipe(None, image=img, flows_bi=flows, generator=gen, **kw).images
+
     def step_resident():
         gen = torch.Generator(device=device).manual_seed(10)  # inference_upscale_a_video.py:197
-        return pipe(None, image=d_image, flows_bi=[d_fw, d_bw], generator=gen, **kw).images
+        return run_pipe(d_image, [d_fw, d_bw], gen)
 
     def step_e2e():
         gen = torch.Generator(device=device).manual_seed(10)
         img = h_image.to(device, non_blocking=True)
         flows = [h_fw.to(device, non_blocking=True), h_bw.to(device, non_blocking=True)]
-        out = pipe(None, image=img, flows_bi=flows, generator=gen, **kw).images
+        out = run_pipe(img, flows, gen)
         h_out.copy_(out, non_blocking=True)
         return out
 
@@ -262,9 +448,12 @@ def main():
     if rank == 0:
         clocks.start()
     l0 = _lib.launch_count()
+    sharding.comm_events_reset(True)
     ms_total = timed(step_resident, args.steps)
+    comm_ms = sharding.comm_events_ms()
+    sharding.comm_events_reset(False)
     launches = _lib.launch_count() - l0
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = None if args.no_e2e else timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
     # roofline of the dominant kernel (tcgen05 implicit GEMM): per-launch CUDA events over one UNet forward
@@ -278,11 +467,14 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         lat = torch.randn(2, 4, 8, H_LR, W_LR, device=device, dtype=torch.float16)
+        lat[1] = lat[0]
         low = torch.randn(2, 3, 8, H_LR, W_LR, device=device, dtype=torch.float16)
+        low[1] = low[0]
         ctx = torch.cat([neg, pos])
-        pipe.unet(lat, 500, low, encoder_hidden_states=ctx, class_labels=torch.tensor([NOISE_LEVEL]))
+        ukw = dict(encoder_hidden_states=ctx, class_labels=torch.tensor([NOISE_LEVEL]), cfg_shared_input=True)
+        pipe.unet(lat, 500, low, **ukw)
         with ops.Profile() as prof:
-            pipe.unet(lat, 500, low, encoder_hidden_states=ctx, class_labels=torch.tensor([NOISE_LEVEL]))
+            pipe.unet(lat, 500, low, **ukw)
         summ = prof.summary()
         ig = summ.get("igemm", dict(flops=0.0, ms=1.0, launches=1))
         tot_ms = sum(d["ms"] for d in summ.values())
@@ -303,39 +495,65 @@ def main():
         rep_ms = e0.elapsed_time(e1) / 10
         rep_flops = 2.0 * 16 * 160 * 288 * 512 * 512 * 9
         burst = peaks.get("bf16_tflops", 1590.0)
+        ncu = _ncu_profile_of_dominant_kernel()
+        hbm = peaks.get("hbm_gbs", 6650.0)
         roof = {"bound": "tensor", "kernel": "uav::igemm_kernel (tcgen05 implicit GEMM: conv2d/conv_t/linear)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                # DRAM bytes of the representative launch below, from `ncu --set full` of the CTA-pair kernel
-                # (profiles/r1_ncu_full_summaries_v2.txt: 759.96 MB read + 718.57 MB written; algorithmic = 755 MB in
-                # + 755 MB out + 4.7 MB weights)
-                "traffic": 1478523648,
+                "traffic": (ncu or {}).get("dram_bytes_per_launch"),
                 "representative_launch": {"op": "conv3x3 512->512, 16 x 160x288 (3.48 TFLOP)", "ms": rep_ms,
                                           "achieved": rep_flops / rep_ms / 1e9, "peak_burst": burst,
                                           "frac_of_burst_peak": rep_flops / rep_ms / 1e9 / burst,
                                           "algorithmic_bytes": 2 * (16 * 160 * 288 * 512 * 2) + 512 * 9 * 512 * 2,
-                                          "ncu_tensor_pipe_active_pct": 81.06},
+                                          "ncu": ncu},
                 "peak_source": which, "launches_per_unet_forward": ig["launches"],
+                "unet_forward_ms": tot_ms,
                 "share_of_unet_forward_time": ig["ms"] / tot_ms,
                 "per_kind_ms": {k: round(d["ms"], 3) for k, d in summ.items()},
-                "hbm_bound_kinds_GBps": {k: round(d["bytes"] / d["ms"] / 1e6, 1) for k, d in summ.items() if d["flops"] == 0.0}}
+                "hbm_bound_kinds": {k: {"GBps": round(d["bytes"] / d["ms"] / 1e6, 1), "frac_of_hbm_peak": round(d["bytes"] / d["ms"] / 1e6 / hbm, 3)}
+                                    for k, d in summ.items() if d["flops"] == 0.0 and d["ms"] > 0},
+                "hbm_peak_GBps": hbm}
+        del lat, low, xr, wr, orr
+        torch.cuda.empty_cache()
 
     if rank == 0:
         fps = T * args.steps / (ms_total / 1000.0)
-        fps_e2e = T * args.steps / (ms_e2e / 1000.0)
-        cb = None if args.no_cpu_baseline or args.gpus != 1 else cpu_baseline_sample()
+        n_uniq = len(sharding.unique(sharding.unet_windows(T)))
         line = {"metric": "upscaled frames/sec (30 DDIM steps, 320x576->4x)", "value": fps, "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "higher_is_better": True, "scaling": "weak" if cfg["frames"] is None else "strong", "vs_baseline": None,
+                "dtype": "f16",
                 "data": "synthetic (seeded LR clip, smooth flows, random prompt embeddings), random-init weights of the shipped configs",
-                "config": {"workload": f"{T}-frame 320x576->1280x2304, {args.ddim_steps} DDIM steps, guidance 6, propagation at {kw['propagation_steps']}, vae_3d decode",
-                           "frames": T, "unet_windows_per_step": T // 6 if T > 8 else 1, "parallelism": f"windows/chunks over {args.gpus} GPU(s)",
+                "config": {"workload": f"{args.config}: {T}-frame {H_LR}x{W_LR}->{4 * H_LR}x{4 * W_LR}, {ddim_steps} DDIM steps, guidance 6, "
+                                       f"propagation at {prop}, {cfg['vae']} decode" + (", 256+64 px tiles" if cfg["tiled"] else ""),
+                           "frames": T, "unet_windows_per_step": n_uniq, "parallelism": f"windows/chunks over {args.gpus} GPU(s)",
                            "l2": "inputs larger than L2 (activations 0.4-4.5 GB per layer)"},
-                "e2e": {"value": fps_e2e, "unit": "frames/s",
-                        "h2d_bytes_per_step": int(h_image.numel() * 4 + h_fw.numel() * 4 + h_bw.numel() * 4),
-                        "d2h_bytes_per_step": int(h_out.numel() * 4)},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
-        if cb is not None:
+        if ms_e2e is not None:
+            line["e2e"] = {"value": T * args.steps / (ms_e2e / 1000.0), "unit": "frames/s",
+                           "h2d_bytes_per_step": int(h_image.numel() * 4 + h_fw.numel() * 4 + h_bw.numel() * 4),
+                           "d2h_bytes_per_step": int(h_out.numel() * 4)}
+        if cfg["frames"] is None and args.gpus > 1:
+            # the reference's 8-frame windows overlap by 2: N windows cover 6N + 2 frames, so weak scaling in FRAMES/s is
+            # bounded by (6N + 2) / (8N) even with perfect window-level scaling
+            line["ideal_efficiency"] = (6 * args.gpus + 2) / (8 * args.gpus)
+        if world > 1:
+            line["comm"] = {"collective": "NCCL all_gather_into_tensor of the windows' predictions, once per DDIM step + once after decode",
+                            "ms_per_step": comm_ms / args.steps, "share_of_step": comm_ms / ms_total}
+    if rank == 0 and args.gpus == 1 and args.config == "c2":
+        del d_image, d_fw, d_bw
+        if not args.no_reference_gpu:
+            pipe = None
+            torch.cuda.empty_cache()
+            try:
+                line["reference_gpu"] = reference_gpu_leg(device, h_image, h_fw, h_bw, pe, ddim_steps, prop)
+                line["reference_gpu"]["speedup_e2e"] = line.get("e2e", line)["value"] / line["reference_gpu"]["value"]
+            except Exception as ex:  # never lose the bench line over the comparison leg
+                line["reference_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        if not args.no_cpu_baseline:
+            cb = cpu_sample(cpu_plan(15.0))
+            cb.pop("seconds", None)
             line["cpu_baseline"] = cb
+    if rank == 0:
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

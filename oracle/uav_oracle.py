@@ -343,14 +343,36 @@ def unet_forward(sd: SD, cfg: dict, sample, timestep, low_res, encoder_hidden_st
 # ------------------------------------------------------------------------------------------------
 # AutoencoderKLVideo (autoencoder_kl_cond_video.py, vae_video.py)
 # ------------------------------------------------------------------------------------------------
+# attention over N = h*w tokens materialises an N x N score matrix per frame in the reference; at the BASELINE frame size
+# (N = 184 320) that is 136 GB per frame, so above ATTN_DENSE_LIMIT score elements the oracle evaluates the SAME softmax
+# row-block by row-block ("exact": identical arithmetic per query row, fp32) or through torch's fused SDPA ("sdpa": what a
+# user of the reference has to enable to run this size at all; used only by bench.py's reference-GPU timing leg).
+ATTN_DENSE_LIMIT = 1 << 28
+ATTN_LARGE_IMPL = "exact"
+ATTN_Q_BLOCK = 4096
+
+
+def _single_head_attention(q, k, v, denom: float):
+    n, nq, _ = q.shape
+    if n * nq * k.shape[1] <= ATTN_DENSE_LIMIT:
+        return torch.softmax((q @ k.transpose(-1, -2)) / denom, dim=-1) @ v
+    if ATTN_LARGE_IMPL == "sdpa":
+        return F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None], scale=1.0 / denom)[:, 0]
+    out = torch.empty_like(q)
+    kt = k.transpose(-1, -2)
+    for i in range(n):
+        for s in range(0, nq, ATTN_Q_BLOCK):
+            out[i, s:s + ATTN_Q_BLOCK] = torch.softmax((q[i, s:s + ATTN_Q_BLOCK] @ kt[i]) / denom, dim=-1) @ v[i]
+    return out
+
+
 def attention_block(sd: SD, p: str, x, groups: int, eps: float):
     """diffusers AttentionBlock, 1 head (in-tree copy diffusers_attention.py:330-381); x: (n c h w)."""
     n, c, h, w = x.shape
     hs = F.group_norm(x, groups, sd[p + ".group_norm.weight"], sd[p + ".group_norm.bias"], eps)
     hs = hs.reshape(n, c, h * w).transpose(1, 2)
     q, k, v = linear(sd, p + ".query", hs), linear(sd, p + ".key", hs), linear(sd, p + ".value", hs)
-    probs = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(c), dim=-1)
-    o = linear(sd, p + ".proj_attn", probs @ v)
+    o = linear(sd, p + ".proj_attn", _single_head_attention(q, k, v, math.sqrt(c)))
     return o.transpose(-1, -2).reshape(n, c, h, w) + x
 
 

@@ -242,3 +242,29 @@ def test_raft_state_dict_keys_match_reference():
     shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "shapes_raft.json")))
     sd = RAFT().state_dict()
     assert {k: list(v.shape) for k, v in sd.items()} == shapes
+
+
+def test_window_units_dealing():
+    """whole windows unless dealing single CFG halves lowers the makespan (sharding.window_units)"""
+    from upscale_a_video_b200 import sharding as S
+    assert S.window_units(1, 1, True) == [(0, -1)]
+    assert S.window_units(11, 1, True) == [(w, -1) for w in range(11)]
+    assert S.window_units(8, 8, True) == [(w, -1) for w in range(8)]          # weak-scaling bench: one window per rank
+    assert S.window_units(11, 8, False) == [(w, -1) for w in range(11)]
+    u = S.window_units(11, 8, True)                                            # 64-frame clip on 8 GPUs: 22 halves, 3 rounds
+    assert u == [(w, h) for w in range(11) for h in (0, 1)]
+    per_rank = [sum(1 for k in range(len(u)) if k % 8 == r) for r in range(8)]
+    assert max(per_rank) == 3 and max(per_rank) * S.HALF_UNIT_COST < 2
+    assert S.window_units(5, 4, True) == [(w, h) for w in range(5) for h in (0, 1)]  # config 3: 10 halves on 4 ranks
+
+
+def test_synthetic_weights_match_the_oracle_rule():
+    """bench.py draws the product's random-init weights with upscale_a_video_b200/synthetic.py and the oracle's with
+    oracle/weights.py: the two rules must give bit-identical tensors"""
+    import json
+    from oracle.weights import make_state_dict
+    from upscale_a_video_b200.synthetic import seeded_state_dict
+    for kind in ("vae_3d", "raft"):
+        shapes = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"shapes_{kind}.json")))
+        a, b = make_state_dict(shapes, 4321), seeded_state_dict(shapes, 4321)
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)

@@ -47,11 +47,16 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+LAST_ACTION = None  # "compiled" | "reused" — what the last build() call did (reported by __graft_entry__.build)
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    global LAST_ACTION
     LIBDIR.mkdir(exist_ok=True)
     stamp = LIBDIR / "build.sha256"
     digest = _digest()
     if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == digest:
+        LAST_ACTION = "reused"  # the shipped binary was built from exactly these sources and flags
         return LIB
     nvcc = _nvcc()
     objdir = LIBDIR / "obj"
@@ -76,6 +81,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(digest)
+    LAST_ACTION = "compiled"
     return LIB
 
 

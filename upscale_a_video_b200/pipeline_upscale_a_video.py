@@ -231,16 +231,29 @@ class VideoUpscalePipeline(ConfigMixin):
             shared = {"cfg_shared_input": True}
         windows = sharding.unet_windows(T)
         uniq = sharding.unique(windows)
+        # work units of a step: whole windows, or single CFG halves of windows when that balances the ranks better
+        units = sharding.window_units(len(uniq), world, can_split=do_cfg and image.shape[0] == 2)
+        split = bool(units) and units[0][1] >= 0
+        pe_half = [prompt_embeds[0:1], prompt_embeds[1:2]] if split else None
         for i, t in enumerate(timesteps):
             lat_in = torch.cat([latents] * 2) if do_cfg else latents
             if T > sharding.SHORT_SEQ:
                 local = {}
-                for ui, (s, e) in enumerate(uniq):
-                    if ui % world == rank:
-                        local[ui] = self.unet(lat_in[:, :, s:e], t, image[:, :, s:e], encoder_hidden_states=prompt_embeds,
-                                              class_labels=denoise_level_t, **shared).sample
-                outs = sharding.all_gather_units(local, len(uniq), (lat_in.shape[0], C_lat, sharding.SHORT_SEQ, H, W),
-                                                 dtype, device, self.process_group)
+                for k, (ui, half) in enumerate(units):
+                    if k % world != rank:
+                        continue
+                    s, e = uniq[ui]
+                    if half < 0:
+                        local[k] = self.unet(lat_in[:, :, s:e], t, image[:, :, s:e], encoder_hidden_states=prompt_embeds,
+                                             class_labels=denoise_level_t, **shared).sample
+                    else:
+                        local[k] = self.unet(lat_in[half:half + 1, :, s:e], t, image[half:half + 1, :, s:e],
+                                             encoder_hidden_states=pe_half[half],
+                                             class_labels=denoise_level_t[half:half + 1]).sample
+                nb = 1 if split else lat_in.shape[0]
+                got = sharding.all_gather_units(local, len(units), (nb, C_lat, sharding.SHORT_SEQ, H, W), dtype, device,
+                                                self.process_group)
+                outs = [torch.cat([got[2 * w], got[2 * w + 1]]) for w in range(len(uniq))] if split else got
                 noise_pred = torch.empty(lat_in.shape[0], C_lat, T, H, W, dtype=dtype, device=device)
                 covered = [False] * T
                 for (s, e) in windows:  # reference loop order (the blend is order dependent)

@@ -59,6 +59,40 @@ def unique(units: Sequence) -> List:
     return uniq
 
 
+# relative cost of a UNet call on ONE classifier-free-guidance half of a window, against the call on both halves (which
+# shares the text-independent prefix, ~3.6 % of the work: unet_video.py `cfg_shared_input`)
+HALF_UNIT_COST = 0.52
+
+
+def window_units(n_windows: int, world: int, can_split: bool) -> List[Tuple[int, int]]:
+    """work units of one DDIM step, in dealing order: (window index, half) with half = -1 for "both CFG halves in one
+    UNet call".  GroupNorm statistics, attention and convolutions never mix batch items, so a window's two halves are
+    independent UNet calls; dealing HALVES turns e.g. 11 windows on 8 ranks from 2 rounds into 3 half-rounds = 1.56.
+    Halves are used only when that lowers the makespan (never for world == 1, never when windows divide evenly)."""
+    if n_windows == 0:
+        return []
+    rounds_full = -(-n_windows // world)
+    rounds_half = -(-2 * n_windows // world)
+    if can_split and world > 1 and rounds_half * HALF_UNIT_COST < rounds_full:
+        return [(w, h) for w in range(n_windows) for h in (0, 1)]
+    return [(w, -1) for w in range(n_windows)]
+
+
+_COMM_EVENTS = None  # list of (start, end) CUDA events while bench.py measures the collective's share of a step
+
+
+def comm_events_reset(on: bool):
+    global _COMM_EVENTS
+    _COMM_EVENTS = [] if on else None
+
+
+def comm_events_ms() -> float:
+    if not _COMM_EVENTS:
+        return 0.0
+    torch.cuda.synchronize()
+    return float(sum(s.elapsed_time(e) for s, e in _COMM_EVENTS))
+
+
 def world_info(group=None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -78,7 +112,14 @@ def all_gather_units(local: Dict[int, torch.Tensor], n_units: int, unit_shape, d
     for slot, i in enumerate(mine):
         send[slot].copy_(local[i])
     recv = torch.empty((world, per_rank, *unit_shape), dtype=dtype, device=device)
+    ev = None
+    if _COMM_EVENTS is not None and device.type == "cuda":
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     dist.all_gather_into_tensor(recv.view(world * per_rank, *unit_shape), send, group=group)
+    if ev is not None:
+        ev[1].record()
+        _COMM_EVENTS.append(ev)
     out = []
     for i in range(n_units):
         out.append(recv[i % world, i // world])

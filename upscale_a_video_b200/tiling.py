@@ -59,6 +59,18 @@ def plan_tiles(h: int, w: int, tile_size: int = 256, overlap: int = 64, scale: i
     return plan
 
 
+_SOLO_GROUPS = {}
+
+
+def _solo_group(rank: int, world: int):
+    """single-rank process groups, created once per world size (new_group is a collective and a communicator that is
+    never destroyed would leak one NCCL communicator per rank per clip)"""
+    if world not in _SOLO_GROUPS:
+        import torch.distributed as dist
+        _SOLO_GROUPS[world] = [dist.new_group([r]) for r in range(world)]  # every rank creates every group
+    return _SOLO_GROUPS[world][rank]
+
+
 @torch.no_grad()
 def upscale_tiled(pipeline, image: torch.Tensor, flows_bi: Optional[list] = None, generator=None, tile_size: int = 256,
                   overlap: int = 64, process_group=None, **pipe_kwargs) -> torch.Tensor:
@@ -79,9 +91,7 @@ def upscale_tiled(pipeline, image: torch.Tensor, flows_bi: Optional[list] = None
     saved_group = pipeline.process_group
     solo = None
     if world > 1:
-        import torch.distributed as dist
-        groups = [dist.new_group([r]) for r in range(world)]  # collective: every rank creates every group
-        solo = groups[rank]
+        solo = _solo_group(rank, world)
     try:
         pipeline.process_group = solo if world > 1 else saved_group
         for i, tl in enumerate(plan):
