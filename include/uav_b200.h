@@ -56,8 +56,9 @@ uint64_t uav_launch_count(void);
 /* Fused epilogue of every implicit-GEMM entry point:
  *   v = acc + bias[n] + rowvec[row / rows_per_vec][n]
  *   v = act(v)            (GEGLU: out[n] = v[n] * gelu(v[n + N/2]), output has N/2 columns)
- *   v = v + residual[row][n]
- *   out[row][n] = (out_dtype) v
+ *   v = v * out_scale + residual[row][n]
+ *   out[row][n] = (out_dtype) v          (fp16 conversions saturate to +-65504 instead of producing inf)
+ *   gn_partial[n / 8][row / 32] += {sum, sum of squares} of the 8 x 32 block of v   (optional, see below)
  * Replaces the separate ATen kernels for "+ temb[:, :, None, None, None]" (resnet.py:272-276),
  * "(input_tensor + hidden_states) / output_scale_factor" (resnet.py:292, scale == 1 in every
  * shipped config), "attn(...) + hidden_states" (attention.py:531,537,549,559,563),
@@ -73,7 +74,22 @@ typedef struct {
   int act;               /* uav_act_t */
   int out_dtype;         /* uav_dtype_t */
   int64_t ld_out;        /* element distance between output rows */
+  /* -- optional extensions; an all-zero tail means "off" ------------------------------------------------ */
+  float out_scale;       /* 0 = 1.  Scale applied before the residual add: lets the VAE decoder keep its residual
+                            stream at 2^-k of the reference's values (fp16 range; every consumer is linear or a
+                            GroupNorm, which is scale invariant once eps is scaled by 2^-2k) */
+  /* GroupNorm statistics of the OUTPUT, produced on the way out so that the consumer's nn.GroupNorm
+   * (resnet.py:267,278) needs no separate read pass: fp32 [n_out / 8][gn_blocks][2] = {sum, sum of squares} over
+   * 8 channels x 32 consecutive rows of an M-tile (block = m_tile * 4 + row / 32 inside the tile; rows outside the
+   * tensor contribute 0).  gn_blocks must equal uav_gn_partial_blocks() of the launch; requires the fp16 TMA-store
+   * epilogue (n_out >= 33, aligned) and no GEGLU.  Deterministic (no atomics). */
+  void* gn_partial;
+  int64_t gn_blocks;
 } uav_epilogue_t;
+
+/* number of 32-row statistics blocks the implicit-GEMM launch over `images` images of `w` x `h` output pixels
+ * produces (4 per M-tile; an M-tile is a tw x th = 128 pixel rectangle of one image, or 128 rows when h == 1) */
+int64_t uav_gn_partial_blocks(int64_t w, int64_t h, int64_t images);
 
 /* out[M][N] = epilogue(a[M][K] @ w[N][K]^T).  a: fp16, row stride lda (K % 8 == 0).
  * Replaces nn.Linear call sites: attention.py:97-106,156,177-178,202,327,355,382,400;
@@ -143,6 +159,27 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
                                 float eps, int silu, void* y, int64_t ld_out, void* workspace,
                                 size_t workspace_bytes, uav_stream_t stream);
 
+/* One producer of the tensor a GroupNorm consumes: the statistics blocks an implicit-GEMM launch wrote through
+ * uav_epilogue_t.gn_partial.  `slabs`: how many statistics slabs (batch items, or frames for the per-frame norm) the
+ * launch's blocks divide into evenly, in order — equal to the consumer's n_outer, or 1 when the same rows serve
+ * every n (a skip tensor computed once for both classifier-free-guidance halves). */
+typedef struct {
+  const void* partial; /* fp32 [C / 8][blocks][2] */
+  int64_t blocks;
+  int64_t C;           /* channels of this source, % 8 == 0 */
+  int64_t slabs;
+} uav_gn_source_t;
+
+/* uav_groupnorm_silu without the statistics read pass: x is the channel concatenation (in order) of up to 4 tensors
+ * whose producers emitted their statistics blocks (the torch.cat of unet_blocks.py:573,645 followed by resnet.py:267).
+ * (C / groups) % 8 == 0.  Two launches (fp64 fixed-order reduction of the blocks, apply) instead of three, and
+ * 2 instead of 3 element passes over x.  workspace: uav_groupnorm_workspace_bytes. */
+uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, int64_t pixels, int64_t C,
+                                              int64_t ld_in, int groups, const float* gamma, const float* beta,
+                                              float eps, int silu, void* y, int64_t ld_out,
+                                              const uav_gn_source_t* sources, int n_sources, void* workspace,
+                                              size_t workspace_bytes, uav_stream_t stream);
+
 /* nn.LayerNorm over the last dim of fp16 tokens (attention.py:457,474,491,494). C % 8 == 0. */
 uav_status_t uav_layernorm(const void* x, int64_t rows, int64_t C, int64_t ld_in,
                            const float* gamma, const float* beta, float eps, void* y,
@@ -192,8 +229,9 @@ uav_status_t uav_channels_last_to_planar(const void* src, int src_dtype, int64_t
                                          int64_t C, int64_t thw, void* dst, int dst_dtype,
                                          int clamp, uav_stream_t stream);
 uav_status_t uav_silu(const void* x, void* y, int64_t n, uav_stream_t stream);
-/* Fuse_sft_block tail (resnet.py:77-78): out = dec + w * (dec * scale + shift); dense fp16, n % 8 == 0 */
-uav_status_t uav_sft_fuse(const void* dec, const void* scale, const void* shift, float w, void* out,
+/* Fuse_sft_block tail (resnet.py:77-78): out = (dec + w * (dec * scale + shift)) * out_scale (0 = 1; the VAE decoder's
+ * residual-stream scale, see uav_epilogue_t.out_scale); dense fp16, n % 8 == 0 */
+uav_status_t uav_sft_fuse(const void* dec, const void* scale, const void* shift, float w, float out_scale, void* out,
                           int64_t n, uav_stream_t stream);
 /* diffusers Timesteps(dim, flip_sin_to_cos, freq_shift) (unet_video.py:173,472): fp32 math, fp16 out */
 uav_status_t uav_timestep_embedding(const float* t, int64_t B, int64_t dim, int flip_sin_to_cos,

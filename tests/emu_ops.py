@@ -14,7 +14,7 @@ import torch.nn.functional as F
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 
 
-def _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype):
+def _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, out_scale=1.0):
     """acc: (..., N) fp32 pre-bias accumulators flattened over rows in the output's row order"""
     n = acc.shape[-1]
     v = acc.reshape(-1, n)
@@ -28,6 +28,8 @@ def _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype):
     elif act == ACT_GEGLU:
         half = n // 2
         v = v[:, :half] * F.gelu(v[:, half:])
+    if out_scale != 1.0:
+        v = v * out_scale
     if residual is not None:
         v = v + residual.float().reshape(-1, residual.shape[-1])[:, :v.shape[-1]]
     return v
@@ -41,9 +43,10 @@ def _finish(v, lead_shape, out, out_dtype):
     return out
 
 
-def linear(a, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
+def linear(a, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16,
+           out_scale=1.0, gn_stats=False):
     acc = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
-    v = _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype)
+    v = _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, out_scale)
     return _finish(v, a.shape[:-1], out, out_dtype)
 
 
@@ -54,7 +57,7 @@ def _conv_nhwc(x4, w, stride, pads):
 
 
 def conv2d(x, w, bias=None, *, stride=1, pad_mode=0, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE,
-           out_dtype=torch.float16):
+           out_dtype=torch.float16, out_scale=1.0, gn_stats=False):
     *lead, H, W, Cin = x.shape
     k = w.shape[1]
     x4 = x.float().reshape(-1, H, W, Cin)
@@ -65,7 +68,7 @@ def conv2d(x, w, bias=None, *, stride=1, pad_mode=0, out=None, residual=None, ro
         y = _conv_nhwc(x4, w, 2, (1, 1, 1, 1))
     else:  # F.pad (0, 1, 0, 1) then no padding
         y = _conv_nhwc(x4, w, 2, (0, 1, 0, 1))
-    v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype)
+    v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, out_scale)
     return _finish(v, (*lead, y.shape[1], y.shape[2]), out, out_dtype)
 
 
@@ -90,23 +93,24 @@ def upsample2x_conv3x3(x, w4, bias=None):
     return out.reshape(*lead, 2 * H, 2 * W, Cout).half()
 
 
-def conv_temporal(x, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
+def conv_temporal(x, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16,
+                  out_scale=1.0, gn_stats=False):
     B, T, H, W, Cin = x.shape
     Cout, k, _ = w.shape
     xp = F.pad(x.float().permute(0, 4, 1, 2, 3), (0, 0, 0, 0, k // 2, k // 2))
     y = F.conv3d(xp, w.float().permute(0, 2, 1)[:, :, :, None, None]).permute(0, 2, 3, 4, 1)
-    v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype)
+    v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, out_scale)
     return _finish(v, (B, T, H, W), out, out_dtype)
 
 
-def conv3d(x, w, bias=None, *, out=None, residual=None, act=ACT_NONE, out_dtype=torch.float16):
+def conv3d(x, w, bias=None, *, out=None, residual=None, act=ACT_NONE, out_dtype=torch.float16, out_scale=1.0, gn_stats=False):
     B, T, H, W, Cin = x.shape
     y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float().permute(0, 4, 1, 2, 3), padding=1).permute(0, 2, 3, 4, 1)
-    v = _epilogue(y, bias, None, 0, residual, act, out, out_dtype)
+    v = _epilogue(y, bias, None, 0, residual, act, out, out_dtype, out_scale)
     return _finish(v, (B, T, H, W), out, out_dtype)
 
 
-def group_norm(x, gamma, beta, groups, eps, *, silu, n_outer, out=None):
+def group_norm(x, gamma, beta, groups, eps, *, silu, n_outer, out=None, stats=None, batch=None):
     C = x.shape[-1]
     v = x.float().reshape(n_outer, -1, C).permute(0, 2, 1)  # (n, C, pixels)
     y = F.group_norm(v, groups, gamma.float(), beta.float(), eps)
@@ -205,9 +209,9 @@ def silu(x):
     return F.silu(x.float()).half()
 
 
-def sft_fuse(dec, scale, shift, w):
+def sft_fuse(dec, scale, shift, w, out_scale=1.0):
     d = dec.float()
-    return (d + w * (d * scale.float() + shift.float())).half()
+    return ((d + w * (d * scale.float() + shift.float())) * out_scale).half()
 
 
 def timestep_embedding(t, dim, flip_sin_to_cos, freq_shift):

@@ -103,6 +103,43 @@ def test_vae_host_logic_vs_golden(emulated):
     assert e < 1e-2
 
 
+def _hot_vae_state_dict(kind):
+    """vae state dict whose up-block branch outputs are ~3e4 x larger: the decoder's residual stream leaves the fp16 range
+    (what the shipped x4-upscaler VAE does: "overflows in float16", pipeline_upscale_a_video.py:667-669)"""
+    from oracle.weights import make_state_dict
+    meta = json.load(open(os.path.join(G, "meta.json")))
+    sd = make_state_dict(json.load(open(os.path.join(G, f"shapes_{kind}.json"))), meta["seed_vae"])
+    for k in sd:
+        if k.startswith("decoder.up_blocks.") and (".conv2." in k or ".conv_3d." in k):
+            sd[k] = sd[k] * 3.0e4
+    return sd
+
+
+@pytest.mark.parametrize("kind", ["vae_3d", "vae_video"])
+def test_vae_decoder_residual_stream_beyond_fp16_range(emulated, monkeypatch, kind):
+    """the scaled residual stream (autoencoder_kl_cond_video.VAE_STREAM_SCALE) keeps the fp16 decoder exact where an
+    unscaled fp16 stream overflows"""
+    from oracle import uav_oracle as O
+    from upscale_a_video_b200 import AutoencoderKLVideo, autoencoder_kl_cond_video as A
+    cfg = json.load(open(os.path.join(CFG, f"{kind}_config.json")))
+    sd = _hot_vae_state_dict(kind)
+    g = torch.Generator().manual_seed(3)
+    z, img = torch.randn(1, 4, 2, 12, 16, generator=g), torch.rand(1, 3, 2, 12, 16, generator=g) * 2 - 1
+    with torch.no_grad():
+        taps = []
+        ref = O.vae_decode(sd, cfg, z, img, 1.0)
+    m = AutoencoderKLVideo.from_config(cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval()
+    out = m.decode(z, img, 1.0).sample
+    e = _rel(out, ref)
+    print(f"\n[{kind} hot residual stream, scale {A.VAE_STREAM_SCALE}] rel L2 err {e:.3e}")
+    assert torch.isfinite(out).all() and e < 1e-2
+    monkeypatch.setattr(A, "VAE_STREAM_SCALE", 1.0)
+    bad = m.decode(z, img, 1.0).sample
+    assert (not torch.isfinite(bad).all()) or _rel(bad, ref) > 10 * e  # the unscaled fp16 stream is what breaks
+
+
 @pytest.mark.parametrize("case", ["c1_t1_64x64", "t11_16x16_prop"])
 def test_pipeline_host_logic_vs_golden(emulated, unet_sd, case):
     """VideoUpscalePipeline.__call__ end to end (window plan incl. the re-anchored last window, blend, CFG, split DDIM step,

@@ -193,3 +193,116 @@ def test_upsample2x_conv3x3(NB, H, W, Cin, Cout):
     ref = F.conv2d(up, w.float().permute(0, 3, 1, 2), b, padding=1).permute(0, 2, 3, 1)
     assert out.shape == ref.shape
     _close(out, ref, Cin * 9, f"upsample2x+conv {NB}x{H}x{W} {Cin}->{Cout}")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: epilogue extensions — output scale, saturating fp16 stores, GroupNorm statistics emitted by the producer
+# ------------------------------------------------------------------------------------------------------------------
+from upscale_a_video_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def _rand(*shape, scale=1.0):
+    return (torch.randn(*shape, device=DEV) * scale).half()
+
+
+def _check(got, ref, atol=2e-3, rtol=2e-3):
+    err = (got.float() - ref.float()).abs()
+    bad = (err > atol + rtol * ref.float().abs()).sum().item()
+    assert bad == 0, f"{bad}/{err.numel()} mismatches, max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
+
+
+def test_out_scale_and_saturation():
+    a, w = _rand(300, 128, scale=1.0), _rand(256, 128, scale=0.1)
+    res = _rand(300, 256, scale=100.0)
+    bias = torch.randn(256, device=DEV)
+    out = ops.linear(a, w, bias, residual=res, out_scale=2.0 ** -5)
+    ref = (a.float() @ w.float().t() + bias) * 2.0 ** -5 + res.float()
+    _check(out, ref)
+    # conv with scale, no residual
+    x, wc = _rand(2, 20, 24, 64), _rand(128, 3, 3, 64, scale=0.05)
+    out = ops.conv2d(x, wc, None, out_scale=0.25)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wc.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) * 0.25
+    _check(out, ref)
+    # fp16 stores saturate instead of producing inf
+    big = ops.linear(_rand(130, 64, scale=30.0), _rand(64, 64, scale=30.0), torch.full((64,), 1e5, device=DEV))
+    assert torch.isfinite(big).all() and big.max().item() == 65504.0
+
+
+def _gn_ref(x, gamma, beta, groups, eps, silu, n_outer):
+    C = x.shape[-1]
+    v = x.float().reshape(n_outer, -1, C).permute(0, 2, 1)
+    y = F.group_norm(v, groups, gamma, beta, eps)
+    if silu:
+        y = F.silu(y)
+    return y.permute(0, 2, 1).reshape(x.shape)
+
+
+@pytest.mark.parametrize("case", ["conv3x3", "conv3x3_big", "conv_t", "linear", "conv1x1_res", "conv3d", "ragged"])
+def test_groupnorm_statistics_from_the_producer_epilogue(case):
+    """the producing GEMM emits {sum, sumsq} blocks of its OUTPUT (uav_epilogue_t.gn_partial); GroupNorm from those
+    blocks == GroupNorm with its own statistics pass (same fp64 finalisation; the fused statistics see the fp32 values
+    before the fp16 rounding, so the two differ by rounding noise only) == torch's group_norm"""
+    torch.manual_seed(3)
+    groups, eps = 32, 1e-5
+    if case == "conv3x3":
+        x, w = _rand(2, 4, 20, 28, 64), _rand(256, 3, 3, 64, scale=0.05)
+        y = ops.conv2d(x, w, torch.randn(256, device=DEV), gn_stats=True)
+        n_outer_list = [2, 8]
+    elif case == "conv3x3_big":  # >= 2 M-tiles per SM: cta_group::2 path, persistent loop, ghost tile (odd tile count)
+        x, w = _rand(1, 7, 80, 84, 64), _rand(128, 3, 3, 64, scale=0.05)   # 385 M-tiles (8 x 16 pixel boxes)
+        y = ops.conv2d(x, w, None, residual=_rand(1, 7, 80, 84, 128), gn_stats=True)
+        n_outer_list = [1, 7]
+    elif case == "conv_t":
+        x, w = _rand(2, 5, 12, 17, 128), _rand(256, 3, 128, scale=0.05)
+        y = ops.conv_temporal(x, w, torch.randn(256, device=DEV), residual=_rand(2, 5, 12, 17, 256), gn_stats=True)
+        n_outer_list = [2, 10]
+    elif case == "linear":
+        x, w = _rand(2, 4, 256, 128), _rand(512, 128, scale=0.1)
+        y = ops.linear(x, w, torch.randn(512, device=DEV), residual=_rand(2, 4, 256, 512), gn_stats=True)
+        n_outer_list = [2, 8]
+    elif case == "conv1x1_res":
+        x, w = _rand(2, 2, 16, 32, 256), _rand(256, 1, 1, 256, scale=0.1)
+        y = ops.conv2d(x, w, torch.randn(256, device=DEV), residual=x, gn_stats=True)
+        n_outer_list = [2, 4]
+    elif case == "conv3d":
+        x, w = _rand(1, 3, 10, 12, 64), _rand(128, 3, 3, 3, 64, scale=0.05)
+        y = ops.conv3d(x, w, torch.randn(128, device=DEV), gn_stats=True, out_scale=0.125)
+        n_outer_list = [1]
+    else:  # rows per slab not a multiple of 128 for a Linear producer: the consumer must fall back to its own pass
+        x, w = _rand(2, 3, 50, 128), _rand(256, 128, scale=0.1)
+        y = ops.linear(x, w, None, gn_stats=True)
+        assert y.uav_gn[0].slabs_for(2, 2) == 0
+        n_outer_list = [2]
+    st = y.uav_gn
+    assert st and st[0].C == y.shape[-1]
+    C = y.shape[-1]
+    gamma, beta = torch.randn(C, device=DEV) * 0.2 + 1, torch.randn(C, device=DEV) * 0.1
+    for n_outer in n_outer_list:
+        fused = ops.group_norm(y, gamma, beta, groups, eps, silu=True, n_outer=n_outer, stats=st, batch=y.shape[0])
+        plain = ops.group_norm(y, gamma, beta, groups, eps, silu=True, n_outer=n_outer)
+        ref = _gn_ref(y, gamma, beta, groups, eps, True, n_outer)
+        assert (fused.float() - plain.float()).abs().max().item() < 4e-3
+        _check(fused, ref, atol=4e-3)
+
+
+def test_groupnorm_statistics_of_a_concat_and_a_broadcast_skip():
+    """torch.cat([x, skip]) -> GroupNorm (unet_blocks.py:573,645 + resnet.py:267): statistics come from BOTH producers;
+    a skip computed once for the two classifier-free-guidance halves (batch 1) serves both slabs; 48 channels per group
+    straddle the concat boundary (1024 + 512 channels)"""
+    torch.manual_seed(4)
+    B, T, H, W = 2, 2, 8, 16
+    xa = ops.conv2d(_rand(B, T, H, W, 64), _rand(1024, 3, 3, 64, scale=0.05), None, gn_stats=True)
+    xb1 = ops.conv2d(_rand(1, T, H, W, 64), _rand(512, 3, 3, 64, scale=0.05), None, gn_stats=True)
+    cat = ops.concat_channels(xa, xb1)  # broadcasts the batch-1 skip
+    assert len(cat.uav_gn) == 2
+    C = 1536
+    gamma, beta = torch.randn(C, device=DEV) * 0.2 + 1, torch.randn(C, device=DEV) * 0.1
+    fused = ops.group_norm(cat, gamma, beta, 32, 1e-5, silu=True, n_outer=B, stats=cat.uav_gn, batch=B)
+    ref = _gn_ref(cat, gamma, beta, 32, 1e-5, True, B)
+    _check(fused, ref, atol=4e-3)
+    rep = ops.repeat_batch(xb1, 2)
+    fused = ops.group_norm(rep, gamma[:512].contiguous(), beta[:512].contiguous(), 32, 1e-5, silu=False, n_outer=2,
+                           stats=rep.uav_gn, batch=2)
+    _check(fused, _gn_ref(rep, gamma[:512], beta[:512], 32, 1e-5, False, 2), atol=4e-3)

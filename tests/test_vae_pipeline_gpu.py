@@ -52,6 +52,38 @@ def test_vae_decode_encode(vaes):
     assert e < 1e-2
 
 
+@pytest.mark.parametrize("kind", ["vae_3d", "vae_video"])
+def test_vae_decoder_residual_stream_beyond_fp16_range(uav_lib, monkeypatch, kind):
+    """the shipped x4-upscaler VAE "overflows in float16" (pipeline_upscale_a_video.py:667-669), i.e. its
+    decoder's residual stream leaves the fp16 range; synthetic weights with 3e4 x larger up-block branch outputs reproduce
+    that.  The scaled residual stream (autoencoder_kl_cond_video.VAE_STREAM_SCALE, exact: every consumer is linear or a
+    GroupNorm) stays within 1e-2 of the fp32 oracle where the unscaled fp16 stream saturates."""
+    from oracle import uav_oracle as O
+    from oracle.weights import make_state_dict
+    from upscale_a_video_b200 import AutoencoderKLVideo, autoencoder_kl_cond_video as A
+    cfg = json.load(open(os.path.join(CFG, f"{kind}_config.json")))
+    sd = make_state_dict(json.load(open(os.path.join(G, f"shapes_{kind}.json"))), META["seed_vae"])
+    for k in sd:
+        if k.startswith("decoder.up_blocks.") and (".conv2." in k or ".conv_3d." in k):
+            sd[k] = sd[k] * 3.0e4
+    g = torch.Generator().manual_seed(3)
+    z, img = torch.randn(1, 4, 2, 24, 40, generator=g), torch.rand(1, 3, 2, 24, 40, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref = O.vae_decode(sd, cfg, z, img, 1.0)
+    m = AutoencoderKLVideo.from_config(cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().cuda()
+    out = m.decode(z.cuda(), img.cuda(), 1.0).sample
+    e = _rel(out, ref)
+    print(f"\n[{kind} hot residual stream, scale {A.VAE_STREAM_SCALE}] rel L2 err {e:.3e}")
+    assert torch.isfinite(out).all() and e < 1e-2
+    monkeypatch.setattr(A, "VAE_STREAM_SCALE", 1.0)
+    bad = m.decode(z.cuda(), img.cuda(), 1.0).sample
+    e_bad = _rel(bad, ref) if torch.isfinite(bad).all() else float("inf")
+    print(f"[{kind} hot residual stream, unscaled fp16 stream] rel L2 err {e_bad:.3e}")
+    assert e_bad > 10 * e
+
+
 @pytest.fixture(scope="module")
 def unet(uav_lib):
     from oracle.weights import make_state_dict

@@ -35,7 +35,15 @@ class Epilogue(C.Structure):
         ("act", C.c_int),
         ("out_dtype", C.c_int),
         ("ld_out", C.c_int64),
+        ("out_scale", C.c_float),
+        ("gn_partial", C.c_void_p),
+        ("gn_blocks", C.c_int64),
     ]
+
+
+class GnSource(C.Structure):
+    """uav_gn_source_t"""
+    _fields_ = [("partial", C.c_void_p), ("blocks", C.c_int64), ("C", C.c_int64), ("slabs", C.c_int64)]
 
 
 I64, I32, P, F32 = C.c_int64, C.c_int, C.c_void_p, C.c_float
@@ -49,6 +57,8 @@ _PROTOS = {
     "uav_conv3d": [P, I64, I64, I64, I64, I64, I64, P, I64, P, EP, P],
     "uav_upsample2x_conv3x3": [P, I64, I64, I64, I64, I64, P, I64, P, EP, P],
     "uav_groupnorm_silu": [P, I64, I64, I64, I64, I32, P, P, F32, I32, P, I64, P, C.c_size_t, P],
+    "uav_groupnorm_silu_from_partials": [P, I64, I64, I64, I64, I32, P, P, F32, I32, P, I64, C.POINTER(GnSource), I32, P,
+                                         C.c_size_t, P],
     "uav_layernorm": [P, I64, I64, I64, P, P, F32, P, I64, P],
     "uav_attention": [P, P, P, P, I64, I32, I32, I64, I64, I64, I64, I64, I64, I64, F32, P],
     "uav_temporal_attention": [P, P, P, P, I64, I64, I64, I32, I32, I64, I64, I64, I64, F32, P, P, P],
@@ -57,7 +67,7 @@ _PROTOS = {
     "uav_planar_to_channels_last": [P, I32, I64, I64, I64, P, I64, I64, F32, P],
     "uav_channels_last_to_planar": [P, I32, I64, I64, I64, I64, P, I32, I32, P],
     "uav_silu": [P, P, I64, P],
-    "uav_sft_fuse": [P, P, P, F32, P, I64, P],
+    "uav_sft_fuse": [P, P, P, F32, F32, P, I64, P],
     "uav_timestep_embedding": [P, I64, I64, I32, F32, P, P],
     "uav_cfg_combine": [P, P, I64, F32, I32, P],
     "uav_window_blend": [P, I64, P, I64, I64, C.c_uint32, I64, I64, I32, P],
@@ -88,6 +98,7 @@ _SPECIAL = {
     "uav_last_error_string": (C.c_char_p, []),
     "uav_launch_count": (C.c_uint64, []),
     "uav_groupnorm_workspace_bytes": (C.c_size_t, [I64, I32]),
+    "uav_gn_partial_blocks": (C.c_int64, [I64, I64, I64]),
     "uav_plane_stats_workspace_bytes": (C.c_size_t, [I64]),
     "uav_instnorm_workspace_bytes": (C.c_size_t, [I64, I64]),
 }

@@ -14,11 +14,22 @@ from typing import Optional, Tuple
 import torch
 from torch import nn
 
+import os
+
 from . import ops
 from ._config import ConfigMixin
 from . import _lib
 from .layers import (Ctx, DownEncoderBlock3D, Fuse_sft_block, InflatedConv3d, PackedModule, ResnetBlock3D_plus,
                      UNetMidBlock3D, UNetMidBlock3D_plus, UpDecoderBlock3D, UpDecoderBlock3D_plus, _gn)
+
+
+# The reference decodes in fp32 because the SD-x4-upscaler VAE "overflows in float16" (pipeline_upscale_a_video.py:667-669):
+# the decoder's RESIDUAL STREAM grows past 65504 in the up blocks.  Every consumer of that stream is either linear
+# (shortcut / upsampler convs, residual adds) or a GroupNorm — scale invariant once its eps is scaled too — so the decoder
+# keeps the stream at 2^-k of the reference's values (fp16 range x 2^k, power-of-two scale = no rounding change) and every
+# branch output (post-GroupNorm, O(1)) is multiplied by 2^-k in the GEMM epilogue that adds it to the stream.  All fp16
+# stores also saturate instead of producing inf.  UAV_VAE_STREAM_SHIFT=0 restores the unscaled stream.
+VAE_STREAM_SCALE = 2.0 ** -int(os.environ.get("UAV_VAE_STREAM_SHIFT", "7"))
 
 
 @dataclass
@@ -122,16 +133,19 @@ class Decoder(nn.Module):
         self.conv_out = InflatedConv3d(block_out_channels[0], out_channels, 3, padding=1)
 
     def forward(self, c: Ctx, z, img=None, w_lr=1.0):
-        x = self.conv_in.run(c, z)
+        s = VAE_STREAM_SCALE
         if self.condition_img:
             assert img is not None, "input img condition when condition_img is True."
+            x = self.conv_in.run(c, z)
             cond = self.condition_in[0](c, img)
             cond = self.condition_in[1](c, cond)
-            x = self.condition_fuse(c, cond, x, w=w_lr)
-        x = self.mid_block(c, x)
+            x = self.condition_fuse(c, cond, x, w=w_lr, out_scale=s)  # the scaled stream starts after the SFT fusion
+        else:
+            x = self.conv_in.run(c, z, out_scale=s)
+        x = self.mid_block(c, x, s)
         for blk in self.up_blocks:
-            x = blk(c, x)
-        x = _gn(c, self.conv_norm_out, x, True, x.shape[0])
+            x = blk(c, x, s)
+        x = _gn(c, self.conv_norm_out, x, True, x.shape[0], s)
         return self.conv_out.run(c, x, out_dtype=torch.float32)
 
 

@@ -105,7 +105,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 // Fuse_sft_block tail (resnet.py:77-78): out = dec + w * (dec * scale + shift), 8 halfs per thread
 __global__ void __launch_bounds__(256)
     sft_fuse_kernel(const __half* __restrict__ dec, const __half* __restrict__ scale,
-                    const __half* __restrict__ shift, float w, __half* __restrict__ out, int64_t n8) {
+                    const __half* __restrict__ shift, float w, float out_scale, __half* __restrict__ out, int64_t n8) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n8;
        i += static_cast<int64_t>(gridDim.x) * 256) {
     const uint4 d = ldg16(dec + i * 8), sc = ldg16(scale + i * 8), sh = ldg16(shift + i * 8);
@@ -117,8 +117,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 a = __half22float2(dh[j]), b = __half22float2(ch[j]), c = __half22float2(hh[j]);
-      __half2 r = __floats2half2_rn(a.x + w * (a.x * b.x + c.x), a.y + w * (a.y * b.y + c.y));
-      ow[j] = *reinterpret_cast<uint32_t*>(&r);
+      ow[j] = pack_half2_sat((a.x + w * (a.x * b.x + c.x)) * out_scale, (a.y + w * (a.y * b.y + c.y)) * out_scale);
     }
     stg16(out + i * 8, o);
   }
@@ -227,12 +226,12 @@ uav_status_t uav_timestep_embedding(const float* t, int64_t B, int64_t dim, int 
   return UAV_OK;
 }
 
-uav_status_t uav_sft_fuse(const void* dec, const void* scale, const void* shift, float w, void* out,
+uav_status_t uav_sft_fuse(const void* dec, const void* scale, const void* shift, float w, float out_scale, void* out,
                           int64_t n, uav_stream_t stream) {
   UAV_REQUIRE(dec && scale && shift && out && n >= 0 && n % 8 == 0, "uav_sft_fuse: bad argument");
   if (n == 0) return UAV_OK;
   sft_fuse_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)dec, (const __half*)scale, (const __half*)shift, w, (__half*)out, n / 8);
+      (const __half*)dec, (const __half*)scale, (const __half*)shift, w, out_scale == 0.f ? 1.f : out_scale, (__half*)out, n / 8);
   UAV_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return UAV_OK;

@@ -107,6 +107,9 @@ struct alignas(64) IgemmParams {
   int32_t act, out_dtype;
   int64_t ld_out;
   void* out;
+  float out_scale;     // applied before the residual add (1 = off)
+  float* gn_partial;   // [n_out / 8][gn_blocks][2] GroupNorm statistics of the output, or nullptr
+  int64_t gn_blocks;
 };
 
 template <int BLOCK_N, bool GEGLU>
@@ -128,10 +131,7 @@ struct IgemmCfg {
   static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + AUX_BYTES + 1024 /*align*/;
 };
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) { return pack_half2_sat(a, b); }
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
 }
@@ -146,6 +146,43 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case UAV_ACT_QUICK_GELU: return x * rcp_ftz(1.0f + ex2_ftz(-2.4554669595930156f * x));  // x * sigmoid(1.702 x)
     default: return x;
   }
+}
+// x = x * alpha + residual
+__device__ __forceinline__ void fma_half8(float (&x)[8], float alpha, const uint4& q) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h2[j]);
+    x[2 * j] = fmaf(x[2 * j], alpha, f.x);
+    x[2 * j + 1] = fmaf(x[2 * j + 1], alpha, f.y);
+  }
+}
+// sum of 8 values per lane over the 32 lanes of a warp in 7 shuffles (transpose-reduce): afterwards lane L holds the
+// total of value index ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1) (every lane of its group of 4)
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
+  bool hi = (lane & 16) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = hi ? v[i] : v[i + 4];
+    const float keep = hi ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  hi = (lane & 8) != 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = hi ? v[i] : v[i + 2];
+    const float keep = hi ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  hi = (lane & 4) != 0;
+  {
+    const float send = hi ? v[0] : v[1];
+    const float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
 }
 __device__ __forceinline__ void add_half8(float (&x)[8], const uint4& q) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&q);
@@ -481,6 +518,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               const int slab = col0 >> 6;
               const int chunk_base = (col0 & 63) >> 3;  // 16-byte chunk index inside the 128B row
               uint8_t* srow = staging + slab * SLAB_BYTES + row * 128;
+              float st[8];  // {sum, sum of squares} of this row's four 8-column groups (GroupNorm statistics)
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float x[8];
@@ -492,7 +530,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
                   }
-                  if (res != nullptr) add_half8(x, rq[g]);
+                  if (res != nullptr) fma_half8(x, p.out_scale, rq[g]);
+                  else if (p.out_scale != 1.0f) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] *= p.out_scale;
+                  }
+                  if (p.gn_partial != nullptr) {
+                    float sm = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      sm += x[j];
+                      sq = fmaf(x[j], x[j], sq);
+                    }
+                    const bool ok = row_ok && (n0 + g * 8 < p.n_out);
+                    st[2 * g] = ok ? sm : 0.f;
+                    st[2 * g + 1] = ok ? sq : 0.f;
+                  }
                 }
                 uint4 o;
                 o.x = pack_half2(x[0], x[1]);
@@ -501,6 +554,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 o.w = pack_half2(x[6], x[7]);
                 const int phys = (chunk_base + g) ^ (row & 7);  // CU_TENSOR_MAP_SWIZZLE_128B
                 *reinterpret_cast<uint4*>(srow + phys * 16) = o;
+              }
+              if constexpr (AUX) {
+                if (p.gn_partial != nullptr) {  // warp-uniform
+                  const float tot = warp_reduce8(st, lane);
+                  const int vi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                  const int oct = (n0 >> 3) + (vi >> 1);
+                  const int64_t blk = static_cast<int64_t>((w / p.n_tiles) * CL + cta_rank) * 4 + quad;
+                  if ((lane & 3) == 0 && blk < p.gn_blocks && oct * 8 < p.n_out)
+                    p.gn_partial[(static_cast<int64_t>(oct) * p.gn_blocks + blk) * 2 + (vi & 1)] = tot;
+                }
               }
             }
             // accumulator fully read: hand it back to the MMA warp
@@ -588,7 +651,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
                   }
-                  if (res != nullptr) add_half8(x, ldg16(res + n));
+                  if (res != nullptr) fma_half8(x, p.out_scale, ldg16(res + n));
+                  else if (p.out_scale != 1.0f) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] *= p.out_scale;
+                  }
                   if (p.out_dtype == UAV_F16) {
                     uint4 o;
                     o.x = pack_half2(x[0], x[1]);
@@ -610,10 +677,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 if (n < p.n_out) {
                   float x = v[j];
                   if (rv != nullptr) x += __half2float(rv[n]);
-                  x = apply_act(x, p.act);
+                  x = apply_act(x, p.act) * p.out_scale;
                   if (res != nullptr) x += __half2float(res[n]);
                   if (p.out_dtype == UAV_F16)
-                    reinterpret_cast<__half*>(p.out)[out_row * p.ld_out + n] = __float2half_rn(x);
+                    reinterpret_cast<__half*>(p.out)[out_row * p.ld_out + n] =
+                        __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
                   else
                     reinterpret_cast<float*>(p.out)[out_row * p.ld_out + n] = x;
                 }
@@ -709,7 +777,8 @@ static uav_status_t launch_instance2(IgemmParams& p, bool cluster, cudaStream_t 
 
 template <int BLOCK_N, bool GEGLU>
 static uav_status_t launch_instance(IgemmParams& p, bool cluster, cudaStream_t stream) {
-  const bool aux = p.rowvec != nullptr || p.residual != nullptr || (p.act != UAV_ACT_NONE && p.act != UAV_ACT_GEGLU);
+  const bool aux = p.rowvec != nullptr || p.residual != nullptr || (p.act != UAV_ACT_NONE && p.act != UAV_ACT_GEGLU) ||
+                   p.out_scale != 1.0f || p.gn_partial != nullptr;
   if constexpr (IgemmCfg<BLOCK_N, GEGLU>::OUT_TILE_N >= 64) {
     if (p.tma_store) {
       return aux ? launch_instance2<BLOCK_N, GEGLU, true, true>(p, cluster, stream)
@@ -843,6 +912,10 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   p.out_dtype = e->out_dtype;
   p.ld_out = e->ld_out;
   p.out = d.out;
+  p.out_scale = e->out_scale == 0.0f ? 1.0f : e->out_scale;
+  p.gn_partial = reinterpret_cast<float*>(e->gn_partial);
+  p.gn_blocks = e->gn_blocks;
+  UAV_REQUIRE(!(geglu && p.out_scale != 1.0f), "igemm: out_scale is not supported with GEGLU");
   UAV_REQUIRE(p.ld_out >= p.n_out, "igemm: ld_out (%lld) < output columns (%d)",
               (long long)p.ld_out, p.n_out);
   UAV_REQUIRE(e->out_dtype == UAV_F16 || e->out_dtype == UAV_F32, "igemm: bad out_dtype");
@@ -857,6 +930,12 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
                        (p.residual == nullptr || (p.ld_res % 8 == 0 && aligned16(p.residual))) &&
                        (p.rowvec == nullptr || (p.ld_rowvec % 8 == 0 && aligned16(p.rowvec)));
   p.tma_store = can_tma ? 1 : 0;
+  if (p.gn_partial != nullptr) {
+    UAV_REQUIRE(can_tma && !geglu && d.out_strides[1] == 0,
+                "igemm: GroupNorm statistics need the dense fp16 TMA-store epilogue (n_out >= 33, 16-byte aligned) without GEGLU");
+    UAV_REQUIRE(p.gn_blocks == (int64_t)m_tiles * 4, "igemm: gn_blocks is %lld, this launch produces %lld blocks",
+                (long long)p.gn_blocks, (long long)m_tiles * 4);
+  }
   UAV_REQUIRE(d.out_strides[1] == 0 || (can_tma && p.residual == nullptr && p.rowvec == nullptr),
               "igemm: a strided output view needs the TMA-store epilogue without residual / row vector");
   if (can_tma) {
@@ -907,7 +986,15 @@ using namespace uav;
 
 extern "C" {
 
-const char* uav_version(void) { return "uav_b200 0.1 (sm_100a)"; }
+int64_t uav_gn_partial_blocks(int64_t w, int64_t h, int64_t images) {
+  if (w <= 0 || h <= 0 || images <= 0) return 0;
+  if (h == 1) return ((w + 127) / 128) * images * 4;
+  uint32_t tw, th;
+  pick_tile_2d(w, h, &tw, &th);
+  return ((w + tw - 1) / tw) * ((h + th - 1) / th) * images * 4;
+}
+
+const char* uav_version(void) { return "uav_b200 0.2 (sm_100a)"; }
 const char* uav_last_error_string(void) { return g_err; }
 uint64_t uav_launch_count(void) { return g_launches.load(); }
 

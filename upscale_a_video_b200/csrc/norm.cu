@@ -9,6 +9,8 @@
 #include "uav_common.cuh"
 
 #include <atomic>
+#include <limits.h>
+#include <string.h>
 
 namespace uav {
 extern std::atomic<uint64_t> g_launches;
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 // lookups per element (the smem version above saturates the LSU pipe at ~3 TB/s).
 __global__ void __launch_bounds__(GN_THREADS)
     gn_apply_vec_kernel(const __half* __restrict__ x, int64_t pixels, int C, int64_t ld_in, int G,
-                        const double* __restrict__ sums, const float* __restrict__ gamma,
+                        const double* __restrict__ sums, int nsplit, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, int silu, __half* __restrict__ y,
                         int64_t ld_out) {
   const int n = blockIdx.y;
@@ -247,8 +249,11 @@ __global__ void __launch_bounds__(GN_THREADS)
   for (int j = 0; j < 8; ++j) {
     const int c = oct * 8 + j;
     const int g = c / cpg;
-    const double s = sums[(static_cast<int64_t>(n) * G + g) * 2];
-    const double q = sums[(static_cast<int64_t>(n) * G + g) * 2 + 1];
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < nsplit; ++k) {  // fixed order: the statistics may arrive as `nsplit` partial sums per group
+      s += sums[((static_cast<int64_t>(n) * G + g) * nsplit + k) * 2];
+      q += sums[((static_cast<int64_t>(n) * G + g) * nsplit + k) * 2 + 1];
+    }
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -271,8 +276,7 @@ __global__ void __launch_bounds__(GN_THREADS)
         a = silu_f(a);
         b = silu_f(b);
       }
-      __half2 r = __floats2half2_rn(a, b);
-      ow[j] = *reinterpret_cast<uint32_t*>(&r);
+      ow[j] = pack_half2_sat(a, b);
     }
     stg16(yn + p * ld_out, o);
   };
@@ -287,6 +291,63 @@ __global__ void __launch_bounds__(GN_THREADS)
     one(p + 3 * stride, v3);
   }
   for (; p < pixels; p += stride) one(p, ldg16(xn + p * ld_in));
+}
+
+// ---------------------------------------------------------------------------------------
+// statistics from the producers' epilogues (igemm.cu: uav_epilogue_t.gn_partial): x is the channel concatenation of up
+// to 4 sources, each with fp32 {sum, sumsq} blocks [C_src / 8][blocks] over 8 channels x 32 rows.  One CTA per
+// (group, n, split) adds its share of the blocks in fp64 in a fixed order -> sums[n][g][split].
+// ---------------------------------------------------------------------------------------
+struct GnSrc {
+  const float2* p;
+  int64_t blocks;     // blocks per octet row
+  int64_t bps;        // blocks per statistics slab
+  int64_t slab_mul;   // 1: slab n starts at n * bps; 0: every n reads the same blocks
+  int oct0, octs;     // octet range of this source inside x
+};
+struct GnReduceParams {
+  GnSrc src[4];
+  int nsrc, oct_per_group, G;
+};
+
+__global__ void __launch_bounds__(256)
+    gn_reduce_partials_kernel(const GnReduceParams prm, double* __restrict__ sums) {
+  __shared__ double sh_s[256], sh_q[256];
+  const int g = blockIdx.x, n = blockIdx.y, sp = blockIdx.z, S = gridDim.z;
+  double s = 0.0, q = 0.0;
+  for (int o = g * prm.oct_per_group; o < (g + 1) * prm.oct_per_group; ++o) {
+    int k = 0;
+    while (k + 1 < prm.nsrc && o >= prm.src[k].oct0 + prm.src[k].octs) ++k;
+    const GnSrc& sr = prm.src[k];
+    const float2* base = sr.p + static_cast<int64_t>(o - sr.oct0) * sr.blocks + static_cast<int64_t>(n) * sr.slab_mul * sr.bps;
+    const int64_t b0 = sr.bps * sp / S, b1 = sr.bps * (sp + 1) / S;
+    int64_t b = b0 + threadIdx.x;
+    for (; b + 768 < b1; b += 1024) {  // 4 loads in flight
+      const float2 v0 = base[b], v1 = base[b + 256], v2 = base[b + 512], v3 = base[b + 768];
+      s += (static_cast<double>(v0.x) + v1.x) + (static_cast<double>(v2.x) + v3.x);
+      q += (static_cast<double>(v0.y) + v1.y) + (static_cast<double>(v2.y) + v3.y);
+    }
+    for (; b < b1; b += 256) {
+      const float2 v = base[b];
+      s += v.x;
+      q += v.y;
+    }
+  }
+  sh_s[threadIdx.x] = s;
+  sh_q[threadIdx.x] = q;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      sh_s[threadIdx.x] += sh_s[threadIdx.x + off];
+      sh_q[threadIdx.x] += sh_q[threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int64_t i = (static_cast<int64_t>(n) * prm.G + g) * S + sp;
+    sums[i * 2] = sh_s[0];
+    sums[i * 2 + 1] = sh_q[0];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -390,6 +451,7 @@ using namespace uav;
 extern "C" {
 
 static constexpr int GN_MAX_BLOCKS_PER_N = 2048;  // upper bound of gridDim.x of the stats kernels
+static constexpr int GN_MAX_SPLIT = 32;            // partial sums per (n, group) of the from-partials path
 
 size_t uav_groupnorm_workspace_bytes(int64_t n_outer, int groups) {
   // fp64 {sum, sumsq} per (n, group)  +  fp32 {sum, sumsq} per (n, block, group)
@@ -454,7 +516,7 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
       int64_t gxa = want < maxb ? want : maxb;
       if (gxa < 1) gxa = 1;
       gn_apply_vec_kernel<<<dim3((unsigned)gxa, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
-          reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums, gamma, beta, eps, silu,
+          reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums, 1, gamma, beta, eps, silu,
           reinterpret_cast<__half*>(y), ld_out);
     } else {
       const int64_t work = pixels * C;
@@ -470,6 +532,69 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
   }
   UAV_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(3, std::memory_order_relaxed);
+  return UAV_OK;
+}
+
+uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, int64_t pixels, int64_t C,
+                                              int64_t ld_in, int groups, const float* gamma, const float* beta,
+                                              float eps, int silu, void* y, int64_t ld_out,
+                                              const uav_gn_source_t* sources, int n_sources, void* workspace,
+                                              size_t workspace_bytes, uav_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UAV_REQUIRE(x && y && gamma && beta && workspace && sources, "uav_groupnorm_silu_from_partials: null pointer");
+  UAV_REQUIRE(n_outer > 0 && n_outer <= 65535 && pixels > 0 && C > 0 && C <= 2048 && groups > 0 && C % groups == 0 &&
+                  ld_in >= C && ld_out >= C,
+              "uav_groupnorm_silu_from_partials: bad shape (C=%lld groups=%d)", (long long)C, groups);
+  const int cpg = (int)(C / groups);
+  UAV_REQUIRE(cpg % 8 == 0, "uav_groupnorm_silu_from_partials: channels per group (%d) must be a multiple of 8", cpg);
+  UAV_REQUIRE(C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+              "uav_groupnorm_silu_from_partials: tensors must be 16-byte aligned with ld %% 8 == 0");
+  UAV_REQUIRE(n_sources >= 1 && n_sources <= 4, "uav_groupnorm_silu_from_partials: 1..4 sources");
+  UAV_REQUIRE(workspace_bytes >= uav_groupnorm_workspace_bytes(n_outer, groups),
+              "uav_groupnorm_silu_from_partials: workspace too small");
+  GnReduceParams prm;
+  memset(&prm, 0, sizeof(prm));
+  int oct = 0;
+  int64_t min_bps = INT64_MAX;
+  for (int i = 0; i < n_sources; ++i) {
+    const uav_gn_source_t& sc = sources[i];
+    UAV_REQUIRE(sc.partial && sc.C > 0 && sc.C % 8 == 0 && sc.blocks > 0 && (sc.slabs == n_outer || sc.slabs == 1) &&
+                    sc.blocks % sc.slabs == 0,
+                "uav_groupnorm_silu_from_partials: bad source %d (C=%lld blocks=%lld slabs=%lld)", i, (long long)sc.C,
+                (long long)sc.blocks, (long long)sc.slabs);
+    prm.src[i].p = reinterpret_cast<const float2*>(sc.partial);
+    prm.src[i].blocks = sc.blocks;
+    prm.src[i].bps = sc.blocks / sc.slabs;
+    prm.src[i].slab_mul = sc.slabs == n_outer ? 1 : 0;
+    prm.src[i].oct0 = oct;
+    prm.src[i].octs = (int)(sc.C / 8);
+    oct += (int)(sc.C / 8);
+    if (prm.src[i].bps < min_bps) min_bps = prm.src[i].bps;
+  }
+  UAV_REQUIRE(oct * 8 == C, "uav_groupnorm_silu_from_partials: sources cover %d channels, x has %lld", oct * 8, (long long)C);
+  prm.nsrc = n_sources;
+  prm.oct_per_group = cpg / 8;
+  prm.G = groups;
+  // enough CTAs to pull the blocks at HBM speed, at least ~256 blocks per split; GN_MAX_SPLIT doubles fit the workspace
+  int64_t S = (4 * (int64_t)num_sms() + groups * n_outer - 1) / (groups * n_outer);
+  if (S > min_bps / 256) S = min_bps / 256;
+  if (S > GN_MAX_SPLIT) S = GN_MAX_SPLIT;
+  if (S < 1) S = 1;
+  double* sums = reinterpret_cast<double*>(workspace);  // [n][g][S][2] <= the stats-kernel partial area
+  gn_reduce_partials_kernel<<<dim3((unsigned)groups, (unsigned)n_outer, (unsigned)S), 256, 0, stream>>>(prm, sums);
+  UAV_CHECK_CUDA(cudaGetLastError());
+  const int octs = (int)(C / 8);
+  const int pix_per_iter = GN_THREADS / octs;
+  int64_t want = ((int64_t)num_sms() * 16 + n_outer - 1) / n_outer;
+  int64_t maxb = (pixels + pix_per_iter * 4 - 1) / (pix_per_iter * 4);
+  int64_t gxa = want < maxb ? want : maxb;
+  if (gxa < 1) gxa = 1;
+  gn_apply_vec_kernel<<<dim3((unsigned)gxa, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
+      reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums, (int)S, gamma, beta, eps, silu,
+      reinterpret_cast<__half*>(y), ld_out);
+  UAV_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return UAV_OK;
 }
 

@@ -309,6 +309,14 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return x * phi;
 }
 
+// fp32 pair -> packed fp16 with saturation to +-65504 (one F2FP.SATFINITE): an activation that leaves the fp16 range
+// clamps instead of becoming inf (which the next GroupNorm would turn into NaN for the whole group)
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // 16-byte global access
 __device__ __forceinline__ uint4 ldg16(const void* p) {
   return *reinterpret_cast<const uint4*>(p);

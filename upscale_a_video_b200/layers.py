@@ -43,8 +43,15 @@ class Packed:
     def clear(self):
         self.cache.clear()
 
-    def conv(self, m: nn.Module):
-        """-> (weight [Cout][taps...][Cin_pad8] fp16, bias fp32 | None)"""
+    def conv(self, m: nn.Module, bias_scale: float = 1.0):
+        """-> (weight [Cout][taps...][Cin_pad8] fp16, bias fp32 | None); `bias_scale`: the bias of a conv that maps a
+        residual stream kept at `bias_scale` x the reference's values onto itself (linear in x: only the bias rescales)"""
+        if bias_scale != 1.0:
+            key = (id(m), "bias_scale", bias_scale)
+            if key not in self.cache:
+                w, b = self.conv(m)
+                self.cache[key] = (w, None if b is None else (b * bias_scale).contiguous())
+            return self.cache[key]
         key = id(m)
         if key not in self.cache:
             w = m.weight.detach()
@@ -144,8 +151,8 @@ class Ctx:
 class InflatedConv3d(nn.Conv2d):
     """resnet.py:94-101 — parameter holder; executed by `ops.conv2d` on (b, t, h, w, c)"""
 
-    def run(self, c: Ctx, x, **epi):
-        w, b = c.pk.conv(self)
+    def run(self, c: Ctx, x, bias_scale: float = 1.0, **epi):
+        w, b = c.pk.conv(self, bias_scale)
         stride = self.stride[0]
         if stride == 2:
             pad_mode = 0 if self.padding[0] == 1 else 1
@@ -172,14 +179,30 @@ class InflatedConv3d(nn.Conv2d):
         return ops.conv2d(x, w, b, **kw, **epi)
 
 
-def _gn(c: Ctx, norm: nn.GroupNorm, x, silu: bool, n_outer: int):
+# the producers of GroupNorm inputs emit the statistics from their epilogues (ops.GnStats); Linear / 1x1 producers are
+# short-K GEMMs whose epilogue is the critical path, so they can be excluded separately (UAV_GN_STATS_LINEAR=0)
+GN_STATS_LINEAR = os.environ.get("UAV_GN_STATS_LINEAR", "1") != "0"
+
+
+def _gn(c: Ctx, norm: nn.GroupNorm, x, silu: bool, n_outer: int, stream_scale: float = 1.0):
+    """`stream_scale`: x holds stream_scale x the reference's values; GroupNorm(s x) with eps s^2 == GroupNorm(x) with eps"""
     g, b = c.pk.affine(norm)
     C = norm.num_channels
+    eps = norm.eps * stream_scale * stream_scale
     if x.shape[-1] != C:  # logical C channels inside a zero-padded buffer (e.g. the 3-channel LR frames)
         out = torch.zeros_like(x)
-        ops.group_norm(x[..., :C], g, b, norm.num_groups, norm.eps, silu=silu, n_outer=n_outer, out=out[..., :C])
+        ops.group_norm(x[..., :C], g, b, norm.num_groups, eps, silu=silu, n_outer=n_outer, out=out[..., :C])
         return out
-    return ops.group_norm(x, g, b, norm.num_groups, norm.eps, silu=silu, n_outer=n_outer)
+    return ops.group_norm(x, g, b, norm.num_groups, eps, silu=silu, n_outer=n_outer, stats=getattr(x, "uav_gn", None),
+                          batch=x.shape[0])
+
+
+def _carry_gn(dst, src):
+    """a reshaped view of a produced tensor keeps the producer's GroupNorm statistics"""
+    st = getattr(src, "uav_gn", None)
+    if st:
+        dst.uav_gn = st
+    return dst
 
 
 class ResnetBlock3D(nn.Module):
@@ -203,22 +226,23 @@ class ResnetBlock3D(nn.Module):
     def _convs(self, c, h, which, **epi):
         return getattr(self, which).run(c, h, **epi)
 
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, stream_scale: float = 1.0):
+        """`stream_scale` (VAE decoder): x and the result are stream_scale x the reference's residual stream"""
         B = x.shape[0]
         thw = x.shape[1] * x.shape[2] * x.shape[3]
-        h = _gn(c, self.norm1, x, True, B)
+        h = _gn(c, self.norm1, x, True, B, stream_scale)
         temb = c.temb(self) if self.time_emb_proj is not None else None
-        h = self._convs(c, h, "conv1", rowvec=temb, rows_per_vec=thw)
+        h = self._convs(c, h, "conv1", rowvec=temb, rows_per_vec=thw, gn_stats=True)
         h = _gn(c, self.norm2, h, True, B)
-        xs = x if self.conv_shortcut is None else self._convs(c, x, "conv_shortcut")
-        return self._convs(c, h, "conv2", residual=xs)
+        xs = x if self.conv_shortcut is None else self._convs(c, x, "conv_shortcut", bias_scale=stream_scale)
+        return self._convs(c, h, "conv2", residual=xs, out_scale=stream_scale, gn_stats=True)
 
 
 class TemporalConv(nn.Conv3d):
     """nn.Conv3d (k,1,1) / (1,1,1) / (3,3,3) parameter holder (resnet.py:332,348,361,461)"""
 
-    def run(self, c: Ctx, x, **epi):
-        w, b = c.pk.conv(self)
+    def run(self, c: Ctx, x, bias_scale: float = 1.0, **epi):
+        w, b = c.pk.conv(self, bias_scale)
         if w.dim() == 3:
             return ops.conv_temporal(x, w, b, **epi)
         epi.pop("rowvec", None)
@@ -256,10 +280,10 @@ class ResnetBlock3D_plus(ResnetBlock3D):
         nn.init.zeros_(self.conv_3d.weight)
         nn.init.zeros_(self.conv_3d.bias)
 
-    def forward(self, c: Ctx, x):
-        out = super().forward(c, x)
-        h = _gn(c, self.norm_3d, out, True, x.shape[0])
-        return self.conv_3d.run(c, h, residual=out)
+    def forward(self, c: Ctx, x, stream_scale: float = 1.0):
+        out = super().forward(c, x, stream_scale)
+        h = _gn(c, self.norm_3d, out, True, x.shape[0], stream_scale)
+        return self.conv_3d.run(c, h, residual=out, out_scale=stream_scale, gn_stats=True)
 
 
 class Upsample3D(nn.Module):
@@ -271,7 +295,7 @@ class Upsample3D(nn.Module):
         self.out_channels = out_channels or channels
         self.conv = InflatedConv3d(channels, self.out_channels, 3, padding=1) if use_conv else None
 
-    def forward(self, c: Ctx, x, output_size=None):
+    def forward(self, c: Ctx, x, output_size=None, stream_scale: float = 1.0):
         assert x.shape[-1] == self.channels
         exact2x = output_size is None or tuple(output_size[-2:]) == (2 * x.shape[-3], 2 * x.shape[-2])
         if (self.conv is not None and exact2x and FUSE_UPSAMPLE_CONV and self.out_channels >= 64
@@ -279,10 +303,10 @@ class Upsample3D(nn.Module):
             # nearest x2 + 3x3 conv as four 2x2 phase convs on the source (4/9 of the MACs, no 4x intermediate)
             w4 = c.pk.tensor(f"up4_{id(self.conv)}",
                              lambda: ops.collapse_upsample_filter(self.conv.weight.detach().permute(0, 2, 3, 1)))
-            _, b = c.pk.conv(self.conv)
+            _, b = c.pk.conv(self.conv, stream_scale)
             return ops.upsample2x_conv3x3(x, w4, b)
         x = ops.upsample_nearest(x, None if output_size is None else tuple(output_size[-2:]))
-        return x if self.conv is None else self.conv.run(c, x)
+        return x if self.conv is None else self.conv.run(c, x, bias_scale=stream_scale, gn_stats=True)
 
 
 class Downsample3D(nn.Module):
@@ -475,7 +499,8 @@ class Transformer3DModel(nn.Module):
         for blk in self.transformer_blocks:
             hs = blk(c, hs)
         w, b = c.pk.linear(self.proj_out)
-        return ops.linear(hs, w, b, residual=x.view(B, T, H * W, C)).view(B, T, H, W, C)
+        out = ops.linear(hs, w, b, residual=x.view(B, T, H * W, C), gn_stats=GN_STATS_LINEAR)
+        return _carry_gn(out.view(B, T, H, W, C), out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -499,7 +524,7 @@ class TemporalModule3D(nn.Module):
     def forward(self, c: Ctx, x):
         h = self.resblocks_3d_temporal(c, x)
         h = self.resblocks_3d_spatial(c, h)
-        return self.shift_conv.run(c, h, residual=x)
+        return self.shift_conv.run(c, h, residual=x, gn_stats=GN_STATS_LINEAR)
 
 
 class EmptyTemporalModule3D(nn.Module):
@@ -639,15 +664,17 @@ class AttentionBlock(nn.Module):
         self.proj_attn = nn.Linear(channels, channels, bias=True)
         self._use_memory_efficient_attention_xformers = False  # read by the pipeline (pipeline...:673)
 
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, stream_scale: float = 1.0):
         B, T, H, W, C = x.shape
-        n = _gn(c, self.group_norm, x, False, B * T)
+        n = _gn(c, self.group_norm, x, False, B * T, stream_scale)
         w, b = c.pk.fused_linear(f"qkv{id(self)}", [self.query, self.key, self.value])
         qkv = ops.linear(n.view(B * T, H * W, C), w, b)
         o = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_heads,
                           scale=(C // self.num_heads) ** -0.5)
         wo, bo = c.pk.linear(self.proj_attn)
-        return ops.linear(o, wo, bo, residual=x.view(B * T, H * W, C)).view(B, T, H, W, C)
+        out = ops.linear(o.view(B, T, H * W, C), wo, bo, residual=x.view(B, T, H * W, C), out_scale=stream_scale,
+                         gn_stats=GN_STATS_LINEAR)
+        return _carry_gn(out.view(B, T, H, W, C), out)
 
 
 def _vae_resnet(plus: bool, cin, cout, eps, groups):
@@ -666,10 +693,10 @@ class UNetMidBlock3D(nn.Module):
         self.attentions = nn.ModuleList([AttentionBlock(in_channels, num_head_channels=attn_num_head_channels,
                                                         eps=resnet_eps, norm_num_groups=resnet_groups)])
 
-    def forward(self, c: Ctx, x):
-        x = self.resnets[0](c, x)
-        x = self.attentions[0](c, x)
-        return self.resnets[1](c, x)
+    def forward(self, c: Ctx, x, stream_scale: float = 1.0):
+        x = self.resnets[0](c, x, stream_scale)
+        x = self.attentions[0](c, x, stream_scale)
+        return self.resnets[1](c, x, stream_scale)
 
 
 class UNetMidBlock3D_plus(UNetMidBlock3D):
@@ -705,11 +732,11 @@ class UpDecoderBlock3D(nn.Module):
                                                   resnet_eps, resnet_groups) for i in range(num_layers)])
         self.upsamplers = nn.ModuleList([Upsample3D(out_channels, True, out_channels)]) if add_upsample else None
 
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, stream_scale: float = 1.0):
         for r in self.resnets:
-            x = r(c, x)
+            x = r(c, x, stream_scale)
         if self.upsamplers is not None:
-            x = self.upsamplers[0](c, x)
+            x = self.upsamplers[0](c, x, None, stream_scale)
         return x
 
 
@@ -727,8 +754,8 @@ class Fuse_sft_block(nn.Module):
         self.scale = InflatedConv3d(dec_ch, dec_ch, 3, 1, 1)
         self.shift = InflatedConv3d(dec_ch, dec_ch, 3, 1, 1)
 
-    def forward(self, c: Ctx, enc_feat, dec_feat, w=1):
+    def forward(self, c: Ctx, enc_feat, dec_feat, w=1, out_scale: float = 1.0):
         e = ops.concat_channels(enc_feat, dec_feat)
         e = self.shared[0](c, e)
         e = self.shared[1](c, e)
-        return ops.sft_fuse(dec_feat, self.scale.run(c, e), self.shift.run(c, e), float(w))
+        return ops.sft_fuse(dec_feat, self.scale.run(c, e), self.shift.run(c, e), float(w), out_scale)

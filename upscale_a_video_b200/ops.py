@@ -95,8 +95,52 @@ def _pixel_ld(x: torch.Tensor) -> int:
     return ld
 
 
-def _epi(out: torch.Tensor, bias=None, rowvec=None, rows_per_vec=0, residual=None, act=ACT_NONE) -> Epilogue:
+class GnStats:
+    """GroupNorm statistics blocks of ONE tensor, written by the epilogue of the implicit-GEMM launch that produced it
+    (uav_epilogue_t.gn_partial): fp32 [C / 8][blocks][2].  `images` x `rows_per_image` is the row geometry of that launch
+    (M-tiles never straddle images), `batch` the number of batch items the tensor spans.  Attached to the produced tensor
+    as `tensor.uav_gn = [GnStats]`; a channel concatenation carries the list of its parts."""
+    __slots__ = ("partial", "blocks", "C", "images", "rows_per_image", "batch")
+
+    def __init__(self, partial, blocks, C, images, rows_per_image, batch):
+        self.partial, self.blocks, self.C = partial, blocks, C
+        self.images, self.rows_per_image, self.batch = images, rows_per_image, batch
+
+    def slabs_for(self, n_outer: int, batch: int) -> int:
+        """number of slabs this source splits into for a consumer normalising `n_outer` slabs over `batch` batch items;
+        0 = unusable (the consumer then runs its own statistics pass)"""
+        per_item = n_outer // batch
+        if self.batch == batch:
+            want = n_outer
+        elif self.batch == 1 and per_item == 1:
+            return 1  # computed once for both classifier-free-guidance halves: every n reads the same blocks
+        else:
+            return 0
+        if self.images % want == 0:
+            return want
+        rows = self.images * self.rows_per_image
+        if self.images == 1 and rows % want == 0 and (rows // want) % 128 == 0:
+            return want
+        return 0
+
+
+GN_FUSED_STATS = __import__("os").environ.get("UAV_GN_FUSED_STATS", "1") != "0"
+
+
+def _gn_request(out: torch.Tensor, n_out: int, w: int, h: int, images: int, batch: int, e: Epilogue):
+    """arm the epilogue to emit the statistics blocks of `out`; returns the GnStats to attach after the launch"""
+    if not GN_FUSED_STATS or out.dtype != torch.float16 or n_out < 64 or n_out % 8:
+        return None
+    blocks = int(_lib.load().uav_gn_partial_blocks(w, h, images))
+    partial = torch.empty(n_out // 8, blocks, 2, dtype=torch.float32, device=out.device)
+    e.gn_partial = partial.data_ptr()
+    e.gn_blocks = blocks
+    return GnStats(partial, blocks, n_out, images, w * h, batch)
+
+
+def _epi(out: torch.Tensor, bias=None, rowvec=None, rows_per_vec=0, residual=None, act=ACT_NONE, out_scale=1.0) -> Epilogue:
     e = Epilogue()
+    e.out_scale = out_scale
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
         e.bias = bias.data_ptr()
@@ -117,7 +161,8 @@ def _epi(out: torch.Tensor, bias=None, rowvec=None, rows_per_vec=0, residual=Non
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out=None,
-           residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
+           residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16, out_scale=1.0,
+           gn_stats=False):
     """out[..., N] = epilogue(a[..., K] @ w[N, K]^T); a fp16 (rows may be a channel-slice view)."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous()
     K = a.shape[-1]
@@ -128,16 +173,19 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if out is None:
         out = torch.empty(*a.shape[:-1], n_out, dtype=out_dtype, device=a.device)
     assert out.shape[-1] == n_out and out.numel() // n_out == M
-    e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
+    e = _epi(out, bias, rowvec, rows_per_vec, residual, act, out_scale)
+    st = _gn_request(out, n_out, M, 1, 1, a.shape[0] if a.dim() > 2 else 1, e) if gn_stats and act != ACT_GEGLU else None
     lib = _lib.load()
     with _timed("igemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out), f"linear M{M} K{K} N{N} act{act}"):
         _lib.check(lib.uav_linear(a.data_ptr(), M, K, _pixel_ld(a) if a.dim() > 1 else K, w.data_ptr(), N,
                                   out.data_ptr(), C.byref(e), _stream()), "uav_linear")
+    if st is not None:
+        out.uav_gn = [st]
     return out
 
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, pad_mode=0, out=None, residual=None,
-           rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
+           rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16, out_scale=1.0, gn_stats=False):
     """x: (..., H, W, Cin) channels-last fp16 (leading dims = images); w: (Cout, k, k, Cin) fp16."""
     assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous()
     *lead, H, W, Cin = x.shape
@@ -150,13 +198,19 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, pad_mode=0,
     if out is None:
         out = torch.empty(*lead, Ho, Wo, Cout, dtype=out_dtype, device=x.device)
     assert tuple(out.shape) == (*lead, Ho, Wo, Cout), (out.shape, (*lead, Ho, Wo, Cout))
-    e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
+    e = _epi(out, bias, rowvec, rows_per_vec, residual, act, out_scale)
+    st = None
+    if gn_stats:
+        st = (_gn_request(out, Cout, NB * Ho * Wo, 1, 1, lead[0] if lead else 1, e) if (k == 1 and stride == 1) else
+              _gn_request(out, Cout, Wo, Ho, NB, lead[0] if lead else 1, e))
     lib = _lib.load()
     with _timed("igemm", 2.0 * NB * Ho * Wo * Cout * Cin * k * k,
                 2.0 * (NB * H * W * Cin + w.numel()) + out.element_size() * NB * Ho * Wo * Cout,
                 f"conv{k}x{k}s{stride} {NB}x{H}x{W} {Cin}->{Cout}"):
         _lib.check(lib.uav_conv2d(x.data_ptr(), NB, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k, stride,
                                   pad_mode, out.data_ptr(), C.byref(e), _stream()), "uav_conv2d")
+    if st is not None:
+        out.uav_gn = [st]
     return out
 
 
@@ -196,7 +250,7 @@ def collapse_upsample_filter(w: torch.Tensor) -> torch.Tensor:
 
 
 def conv_temporal(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=None, rowvec=None,
-                  rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16):
+                  rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16, out_scale=1.0, gn_stats=False):
     """x: (B, T, H, W, Cin); w: (Cout, k, Cin) — nn.Conv3d (k,1,1), zero padding (k-1)/2 in t."""
     assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous()
     B, T, H, W, Cin = x.shape
@@ -204,17 +258,20 @@ def conv_temporal(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, resi
     assert Cin_w == Cin
     if out is None:
         out = torch.empty(B, T, H, W, Cout, dtype=out_dtype, device=x.device)
-    e = _epi(out, bias, rowvec, rows_per_vec, residual, act)
+    e = _epi(out, bias, rowvec, rows_per_vec, residual, act, out_scale)
+    st = _gn_request(out, Cout, H * W, 1, B * T, B, e) if gn_stats else None
     lib = _lib.load()
     with _timed("igemm", 2.0 * B * T * H * W * Cout * Cin * k, 2.0 * (x.numel() + w.numel() + B * T * H * W * Cout),
                 f"conv_t{k} {B}x{T}x{H}x{W} {Cin}->{Cout}"):
         _lib.check(lib.uav_conv_temporal(x.data_ptr(), B, T, H * W, Cin, _pixel_ld(x), w.data_ptr(), Cout, k,
                                          out.data_ptr(), C.byref(e), _stream()), "uav_conv_temporal")
+    if st is not None:
+        out.uav_gn = [st]
     return out
 
 
 def conv3d(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=None, act=ACT_NONE,
-           out_dtype=torch.float16):
+           out_dtype=torch.float16, out_scale=1.0, gn_stats=False):
     """x: (B, T, H, W, Cin); w: (Cout, 3, 3, 3, Cin) — nn.Conv3d 3x3x3, padding 1."""
     assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous()
     B, T, H, W, Cin = x.shape
@@ -222,11 +279,14 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=No
     assert tuple(w.shape) == (Cout, 3, 3, 3, Cin)
     if out is None:
         out = torch.empty(B, T, H, W, Cout, dtype=out_dtype, device=x.device)
-    e = _epi(out, bias, None, 0, residual, act)
+    e = _epi(out, bias, None, 0, residual, act, out_scale)
+    st = _gn_request(out, Cout, W, H, B * T, B, e) if gn_stats else None
     lib = _lib.load()
     with _timed("igemm", 2.0 * B * T * H * W * Cout * Cin * 27, 2.0 * (x.numel() + w.numel() + B * T * H * W * Cout)):
         _lib.check(lib.uav_conv3d(x.data_ptr(), B, T, H, W, Cin, _pixel_ld(x), w.data_ptr(), Cout,
                                   out.data_ptr(), C.byref(e), _stream()), "uav_conv3d")
+    if st is not None:
+        out.uav_gn = [st]
     return out
 
 
@@ -246,9 +306,11 @@ def _gn_workspace(device, nbytes):
 
 
 def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *, silu: bool,
-               n_outer: int, out: Optional[torch.Tensor] = None):
+               n_outer: int, out: Optional[torch.Tensor] = None, stats=None, batch: Optional[int] = None):
     """x: channels-last (..., C) fp16; statistics per (outer index, group) where the leading `n_outer` slabs of
-    x.numel()/C/n_outer pixels each are normalised independently (5-D GN: n_outer=b; per-frame GN: n_outer=b*t)."""
+    x.numel()/C/n_outer pixels each are normalised independently (5-D GN: n_outer=b; per-frame GN: n_outer=b*t).
+    `stats`: list of GnStats of the tensors x is the channel concatenation of (emitted by their producers' epilogues):
+    the statistics read pass is then skipped."""
     assert x.dtype == torch.float16 and gamma.dtype == torch.float32 and beta.dtype == torch.float32
     C = x.shape[-1]
     total_pix = x.numel() // C
@@ -259,6 +321,21 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     lib = _lib.load()
     nbytes = lib.uav_groupnorm_workspace_bytes(n_outer, groups)
     ws = _gn_workspace(x.device, nbytes)
+    srcs = None
+    if stats and (C // groups) % 8 == 0 and len(stats) <= 4 and sum(s.C for s in stats) == C:
+        b = x.shape[0] if batch is None else batch
+        slabs = [s.slabs_for(n_outer, b) for s in stats]
+        if all(slabs):
+            srcs = (_lib.GnSource * len(stats))()
+            for i, (s, sl) in enumerate(zip(stats, slabs)):
+                srcs[i].partial, srcs[i].blocks, srcs[i].C, srcs[i].slabs = s.partial.data_ptr(), s.blocks, s.C, sl
+    if srcs is not None:
+        with _timed("groupnorm", 0.0, 2.0 * 2 * total_pix * C, f"gn(fused stats) {total_pix}px C{C}"):  # read + write
+            _lib.check(lib.uav_groupnorm_silu_from_partials(x.data_ptr(), n_outer, pixels, C, _pixel_ld(x), groups,
+                                                            gamma.data_ptr(), beta.data_ptr(), eps, 1 if silu else 0,
+                                                            out.data_ptr(), _pixel_ld(out), srcs, len(stats), ws.data_ptr(),
+                                                            ws.numel(), _stream()), "uav_groupnorm_silu_from_partials")
+        return out
     with _timed("groupnorm", 0.0, 2.0 * 3 * total_pix * C, f"gn {total_pix}px C{C}"):  # read (stats) + read + write
         _lib.check(lib.uav_groupnorm_silu(x.data_ptr(), n_outer, pixels, C, _pixel_ld(x), groups, gamma.data_ptr(),
                                           beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), _pixel_ld(out),
@@ -343,6 +420,9 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor):
             copy_channels(b, out[i:i + 1, ..., a.shape[-1]:])
     else:
         copy_channels(b, out[..., a.shape[-1]:])
+    ga, gb = getattr(a, "uav_gn", None), getattr(b, "uav_gn", None)
+    if ga and gb:
+        out.uav_gn = list(ga) + list(gb)
     return out
 
 
@@ -352,6 +432,8 @@ def repeat_batch(x: torch.Tensor, n: int):
     out = torch.empty(n, *x.shape[1:], dtype=x.dtype, device=x.device)
     for i in range(n):
         copy_channels(x, out[i:i + 1])
+    if getattr(x, "uav_gn", None):
+        out.uav_gn = x.uav_gn  # batch-1 statistics serve every batch item (GnStats.slabs_for)
     return out
 
 
@@ -402,13 +484,13 @@ def silu(x: torch.Tensor):
     return out
 
 
-def sft_fuse(dec: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, w: float):
-    """dec + w * (dec * scale + shift) (Fuse_sft_block, resnet.py:77-78); dense fp16 tensors of equal shape"""
+def sft_fuse(dec: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, w: float, out_scale: float = 1.0):
+    """(dec + w * (dec * scale + shift)) * out_scale (Fuse_sft_block, resnet.py:77-78); dense fp16 tensors of equal shape"""
     for t in (dec, scale, shift):
         assert t.dtype == torch.float16 and t.is_contiguous() and t.shape == dec.shape
     out = torch.empty_like(dec)
     lib = _lib.load()
-    _lib.check(lib.uav_sft_fuse(dec.data_ptr(), scale.data_ptr(), shift.data_ptr(), float(w), out.data_ptr(), dec.numel(),
+    _lib.check(lib.uav_sft_fuse(dec.data_ptr(), scale.data_ptr(), shift.data_ptr(), float(w), float(out_scale), out.data_ptr(), dec.numel(),
                                 _stream()), "uav_sft_fuse")
     return out
 
