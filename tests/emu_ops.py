@@ -77,20 +77,25 @@ def collapse_upsample_filter(w):
     return real_ops.collapse_upsample_filter(w)
 
 
-def upsample2x_conv3x3(x, w4, bias=None):
+def upsample2x_conv3x3(x, w4, bias=None, out=None):
     """phase p = a*2+b -> output pixel (2y+a, 2x+b); taps read rows {y-1, y} (a=0) or {y, y+1} (a=1), columns likewise"""
     *lead, H, W, Cin = x.shape
     Cout = w4.shape[1]
     x4 = x.float().reshape(-1, H, W, Cin)
-    out = torch.zeros(x4.shape[0], 2 * H, 2 * W, Cout)
+    out_, out = out, torch.zeros(x4.shape[0], 2 * H, 2 * W, Cout)
     for a in range(2):
         for b in range(2):
             pads = (1 - b, b, 1 - a, a)  # left, right, top, bottom
             y = _conv_nhwc(x4, w4[a * 2 + b], 1, pads)
             out[:, a::2, b::2] = y
+    acc = out
     if bias is not None:
-        out = out + bias.float()
-    return out.reshape(*lead, 2 * H, 2 * W, Cout).half()
+        acc = acc + bias.float()
+    res = acc.reshape(*lead, 2 * H, 2 * W, Cout).half()
+    if out_ is not None:
+        out_.copy_(res)
+        return out_
+    return res
 
 
 def conv_temporal(x, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16,

@@ -198,11 +198,47 @@ def _gn(c: Ctx, norm: nn.GroupNorm, x, silu: bool, n_outer: int, stream_scale: f
 
 
 def _carry_gn(dst, src):
-    """a reshaped view of a produced tensor keeps the producer's GroupNorm statistics"""
-    st = getattr(src, "uav_gn", None)
-    if st:
-        dst.uav_gn = st
+    """a reshaped view of a produced tensor keeps the producer's GroupNorm statistics and its concat-buffer membership"""
+    for name in ("uav_gn", "uav_cat"):
+        st = getattr(src, name, None)
+        if st is not None:
+            setattr(dst, name, st)
     return dst
+
+
+# skip-connection concat without the copy of the main branch (unet_blocks.py:573,645 `torch.cat([hidden_states,
+# res_hidden_states], dim=1)`): the concat buffer is allocated BEFORE the layer that produces hidden_states runs, the skip
+# is copied into its tail (a skip computed once for both classifier-free-guidance halves is broadcast there) and the
+# producer's epilogue stores straight into the head slice (`out=`).  UAV_INPLACE_CONCAT=0: two copies, as in round 1.
+INPLACE_CONCAT = os.environ.get("UAV_INPLACE_CONCAT", "1") != "0"
+
+
+def new_cat_slot(skip, cx: int, batch: int):
+    """-> the head slice (batch, t, h, w, cx) of a fresh concat buffer whose tail already holds `skip`; the producer of
+    the main branch writes into it and `cat_with_skip` later returns the whole buffer"""
+    if not INPLACE_CONCAT:
+        return None
+    cs = skip.shape[-1]
+    buf = torch.empty(batch, *skip.shape[1:-1], cx + cs, dtype=skip.dtype, device=skip.device)
+    if skip.shape[0] == 1 and batch > 1:
+        for i in range(batch):
+            ops.copy_channels(skip, buf[i:i + 1, ..., cx:])
+    else:
+        ops.copy_channels(skip, buf[..., cx:])
+    slot = buf[..., :cx]
+    slot.uav_cat = (buf, skip)
+    return slot
+
+
+def cat_with_skip(x, skip):
+    cat = getattr(x, "uav_cat", None)
+    if cat is not None and cat[1] is skip:
+        buf = cat[0]
+        ga, gb = getattr(x, "uav_gn", None), getattr(skip, "uav_gn", None)
+        if ga and gb:
+            buf.uav_gn = list(ga) + list(gb)
+        return buf
+    return ops.concat_channels(x, skip)
 
 
 class ResnetBlock3D(nn.Module):
@@ -226,8 +262,9 @@ class ResnetBlock3D(nn.Module):
     def _convs(self, c, h, which, **epi):
         return getattr(self, which).run(c, h, **epi)
 
-    def forward(self, c: Ctx, x, stream_scale: float = 1.0):
-        """`stream_scale` (VAE decoder): x and the result are stream_scale x the reference's residual stream"""
+    def forward(self, c: Ctx, x, stream_scale: float = 1.0, out=None):
+        """`stream_scale` (VAE decoder): x and the result are stream_scale x the reference's residual stream;
+        `out`: destination view (e.g. the head slice of the next concat buffer)"""
         B = x.shape[0]
         thw = x.shape[1] * x.shape[2] * x.shape[3]
         h = _gn(c, self.norm1, x, True, B, stream_scale)
@@ -235,7 +272,7 @@ class ResnetBlock3D(nn.Module):
         h = self._convs(c, h, "conv1", rowvec=temb, rows_per_vec=thw, gn_stats=True)
         h = _gn(c, self.norm2, h, True, B)
         xs = x if self.conv_shortcut is None else self._convs(c, x, "conv_shortcut", bias_scale=stream_scale)
-        return self._convs(c, h, "conv2", residual=xs, out_scale=stream_scale, gn_stats=True)
+        return self._convs(c, h, "conv2", residual=xs, out_scale=stream_scale, gn_stats=True, out=out)
 
 
 class TemporalConv(nn.Conv3d):
@@ -295,7 +332,7 @@ class Upsample3D(nn.Module):
         self.out_channels = out_channels or channels
         self.conv = InflatedConv3d(channels, self.out_channels, 3, padding=1) if use_conv else None
 
-    def forward(self, c: Ctx, x, output_size=None, stream_scale: float = 1.0):
+    def forward(self, c: Ctx, x, output_size=None, stream_scale: float = 1.0, out=None):
         assert x.shape[-1] == self.channels
         exact2x = output_size is None or tuple(output_size[-2:]) == (2 * x.shape[-3], 2 * x.shape[-2])
         if (self.conv is not None and exact2x and FUSE_UPSAMPLE_CONV and self.out_channels >= 64
@@ -304,9 +341,12 @@ class Upsample3D(nn.Module):
             w4 = c.pk.tensor(f"up4_{id(self.conv)}",
                              lambda: ops.collapse_upsample_filter(self.conv.weight.detach().permute(0, 2, 3, 1)))
             _, b = c.pk.conv(self.conv, stream_scale)
-            return ops.upsample2x_conv3x3(x, w4, b)
+            return ops.upsample2x_conv3x3(x, w4, b, out=out)
         x = ops.upsample_nearest(x, None if output_size is None else tuple(output_size[-2:]))
-        return x if self.conv is None else self.conv.run(c, x, bias_scale=stream_scale, gn_stats=True)
+        if self.conv is None:
+            assert out is None
+            return x
+        return self.conv.run(c, x, bias_scale=stream_scale, gn_stats=True, out=out)
 
 
 class Downsample3D(nn.Module):
@@ -490,7 +530,7 @@ class Transformer3DModel(nn.Module):
             for _ in range(num_layers)])
         self.proj_out = nn.Linear(in_channels, inner)
 
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, out=None):
         B, T, H, W, C = x.shape
         x = self.resblock_temporal(c, x)
         hs = _gn(c, self.norm, x, False, B * T)
@@ -499,8 +539,11 @@ class Transformer3DModel(nn.Module):
         for blk in self.transformer_blocks:
             hs = blk(c, hs)
         w, b = c.pk.linear(self.proj_out)
-        out = ops.linear(hs, w, b, residual=x.view(B, T, H * W, C), gn_stats=GN_STATS_LINEAR)
-        return _carry_gn(out.view(B, T, H, W, C), out)
+        dst = None if out is None else out.view(B, T, H * W, C)
+        y = ops.linear(hs, w, b, residual=x.view(B, T, H * W, C), gn_stats=GN_STATS_LINEAR, out=dst)
+        if out is not None:
+            return _carry_gn(out, y)
+        return _carry_gn(y.view(B, T, H, W, C), y)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -521,14 +564,15 @@ class TemporalModule3D(nn.Module):
         nn.init.zeros_(self.shift_conv.weight)
         nn.init.zeros_(self.shift_conv.bias)
 
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, out=None):
         h = self.resblocks_3d_temporal(c, x)
         h = self.resblocks_3d_spatial(c, h)
-        return self.shift_conv.run(c, h, residual=x, gn_stats=GN_STATS_LINEAR)
+        return self.shift_conv.run(c, h, residual=x, gn_stats=GN_STATS_LINEAR, out=out)
 
 
 class EmptyTemporalModule3D(nn.Module):
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, out=None):
+        assert out is None
         return x
 
 
@@ -598,10 +642,10 @@ class UNetMidBlock3DCrossAttn(nn.Module):
                                               False, rotary_emb)])
         self.resnets = nn.ModuleList([mk(), mk()])
 
-    def forward(self, c: Ctx, x):
+    def forward(self, c: Ctx, x, out=None):
         x = self.resnets[0](c, x)
         x = self.attentions[0](c, x)
-        return self.resnets[1](c, x)
+        return self.resnets[1](c, x, out=out)
 
 
 class UpBlock3D(nn.Module):
@@ -621,14 +665,22 @@ class UpBlock3D(nn.Module):
         self.attentions = None
         self.upsamplers = nn.ModuleList([Upsample3D(out_channels, True, out_channels)]) if add_upsample else None
 
-    def forward(self, c: Ctx, x, skips, upsample_size=None):
+    def forward(self, c: Ctx, x, skips, upsample_size=None, out=None):
+        """`out`: destination of the block's result (the head slice of the NEXT concat buffer, see new_cat_slot)"""
+        n = len(self.resnets)
+        B = x.shape[0]
         for i, r in enumerate(self.resnets):
-            x = ops.concat_channels(x, skips[-1 - i])
-            x = r(c, x)
+            x = cat_with_skip(x, skips[-1 - i])
+            last = i == n - 1
+            # the main branch of the next concat is produced by this stage's last layer: let it store there directly
+            nxt = (out if self.upsamplers is None else None) if last else new_cat_slot(skips[-2 - i], r.out_channels, B)
             if self.attentions is not None:
-                x = self.attentions[i](c, x)
+                x = r(c, x)
+                x = self.attentions[i](c, x, out=nxt)
+            else:
+                x = r(c, x, out=nxt)
         if self.upsamplers is not None:
-            x = self.upsamplers[0](c, x, upsample_size)
+            x = self.upsamplers[0](c, x, upsample_size, out=out)
         return x
 
 

@@ -214,7 +214,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, pad_mode=0,
     return out
 
 
-def upsample2x_conv3x3(x: torch.Tensor, w4: torch.Tensor, bias=None):
+def upsample2x_conv3x3(x: torch.Tensor, w4: torch.Tensor, bias=None, out=None):
     """nearest x2 upsample + 3x3 conv without the upsampled intermediate.  x: (..., H, W, Cin); w4: (4, Cout, 2, 2, Cin)
     phase filters from `collapse_upsample_filter`."""
     assert x.dtype == torch.float16 and w4.dtype == torch.float16 and w4.is_contiguous()
@@ -224,7 +224,9 @@ def upsample2x_conv3x3(x: torch.Tensor, w4: torch.Tensor, bias=None):
     NB = 1
     for d in lead:
         NB *= d
-    out = torch.empty(*lead, 2 * H, 2 * W, Cout, dtype=torch.float16, device=x.device)
+    if out is None:
+        out = torch.empty(*lead, 2 * H, 2 * W, Cout, dtype=torch.float16, device=x.device)
+    assert tuple(out.shape) == (*lead, 2 * H, 2 * W, Cout) and out.dtype == torch.float16
     e = _epi(out, bias)
     lib = _lib.load()
     with _timed("igemm", 2.0 * NB * 4 * H * W * Cout * Cin * 4, 2.0 * (NB * H * W * Cin + w4.numel() + out.numel()),

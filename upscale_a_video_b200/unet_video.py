@@ -28,7 +28,7 @@ from . import _lib
 from ._lib import UavError
 from .layers import (CrossAttention, CrossAttnDownBlock3D, CrossAttnUpBlock3D, Ctx, DownBlock3D, EmptyTemporalModule3D,
                      InflatedConv3d, PackedModule, ResnetBlock3D, RotaryEmbedding, TemporalModule3D,
-                     UNetMidBlock3DCrossAttn, UpBlock3D, _gn)
+                     UNetMidBlock3DCrossAttn, UpBlock3D, _gn, new_cat_slot)
 
 
 @dataclass
@@ -279,18 +279,35 @@ class UNetVideoModel(PackedModule, ConfigMixin):
             _tap(f"down{i}", x)
             x = tmod(c, x)
             _tap(f"down_temp{i}", x)
-        x = self.mid_block(c, x)
+        # every up-block resnet consumes torch.cat([x, skip]): the layer that produces x stores straight into the head of the
+        # concat buffer (layers.new_cat_slot), so only the skip half is ever copied
+        def first_slot(i, cx, size_hw=None):
+            """head slice of the concat buffer of up block i's first resnet (None: plain allocation by the producer)"""
+            skip = skips[-1]
+            if size_hw is not None and tuple(skip.shape[2:4]) != tuple(size_hw):
+                return None
+            return new_cat_slot(skip, cx, B)
+
+        mid_empty = isinstance(self.mid_temp_block, EmptyTemporalModule3D)
+        c_mid = cfg.block_out_channels[-1]
+        slot = first_slot(0, c_mid, x.shape[2:4])
+        x = self.mid_block(c, x, out=slot if mid_empty else None)
         _tap("mid", x)
-        x = self.mid_temp_block(c, x)
+        x = self.mid_temp_block(c, x, out=None if mid_empty else slot)
         _tap("mid_temp", x)
         for i, (blk, tmod) in enumerate(zip(self.up_blocks, self.up_temp_blocks)):
             nres = len(blk.resnets)
             res, skips = skips[-nres:], skips[:-nres]
             final = i == len(self.up_blocks) - 1
             up_size = tuple(skips[-1].shape[1:4]) if (not final and forward_upsample_size) else None
-            x = blk(c, x, res, up_size)
+            t_empty = isinstance(tmod, EmptyTemporalModule3D)
+            slot = None
+            if not final:
+                hw = tuple(up_size[1:]) if up_size is not None else (2 * x.shape[2], 2 * x.shape[3])
+                slot = first_slot(i + 1, blk.resnets[-1].out_channels, hw)
+            x = blk(c, x, res, up_size, out=slot if t_empty else None)
             _tap(f"up{i}", x)
-            x = tmod(c, x)
+            x = tmod(c, x, out=None if t_empty else slot)
             _tap(f"up_temp{i}", x)
         x = _gn(c, self.conv_norm_out, x, True, B)
         x = self.conv_out.run(c, x)
