@@ -306,3 +306,22 @@ def test_groupnorm_statistics_of_a_concat_and_a_broadcast_skip():
     fused = ops.group_norm(rep, gamma[:512].contiguous(), beta[:512].contiguous(), 32, 1e-5, silu=False, n_outer=2,
                            stats=rep.uav_gn, batch=2)
     _check(fused, _gn_ref(rep, gamma[:512], beta[:512], 32, 1e-5, False, 2), atol=4e-3)
+
+
+@pytest.mark.parametrize("M,K,N", [(148 * 2 * 128 + 77, 512, 512), (40000, 128, 320), (5000, 256, 192)])
+def test_residual_tile_through_tma(M, K, N):
+    """the residual operand arrives as a TMA tile in shared memory (one tile ahead for single-tap GEMMs, in the staging
+    tile for convolutions): residual = channel slice of a wider buffer, ragged last M-tile, N not a multiple of the tile"""
+    a, w = _rand(M, K), _rand(N, K, scale=0.05)
+    wide = _rand(M, N + 64)
+    res = wide[:, 64:]
+    out = ops.linear(a, w, None, residual=res, out_scale=0.5)
+    _close(out, (a.float() @ w.float().t()) * 0.5 + res.float(), K, f"linear+res(slice) {M}x{K}x{N}")
+    # convolution, residual in place of the staging tile, output written over a slice of a wider buffer
+    x, wc = _rand(3, 40, 52, 64), _rand(192, 3, 3, 64, scale=0.05)
+    r = _rand(3, 40, 52, 192)
+    buf = torch.zeros(3, 40, 52, 256, device=DEV, dtype=torch.float16)
+    ops.conv2d(x, wc, None, residual=r, out=buf[..., 64:])
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wc.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) + r.float()
+    _close(buf[..., 64:], ref, 576, "conv+res -> slice")
+    assert buf[..., :64].abs().max().item() == 0

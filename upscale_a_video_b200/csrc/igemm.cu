@@ -86,6 +86,7 @@ struct alignas(64) IgemmParams {
   CUtensorMap map_a;
   CUtensorMap map_b;
   CUtensorMap map_out;           // only valid when tma_store != 0
+  CUtensorMap map_res;           // residual operand as a TMA tensor (same box geometry as map_out); valid when res_mode != 0
   int32_t tap_off[MAX_TAPS][5];  // coordinate offset of each tap (dim0 = channel offset)
   int32_t num_taps;
   int32_t kblocks_per_tap;
@@ -99,6 +100,11 @@ struct alignas(64) IgemmParams {
   int32_t N;      // rows of B
   int32_t n_out;  // output columns (N, or N/2 with GEGLU)
   int32_t tma_store;
+  // residual operand of the TMA-store epilogue: 1 = loaded into the output staging tile itself as soon as the previous
+  // store released it (multi-tap convolutions: the epilogue waits for the accumulator anyway, so the load hides behind the
+  // main loop and costs no shared memory); 2 = loaded ONE TILE AHEAD into a dedicated buffer carved from the end of the
+  // ring (single-tap GEMMs: HBM / epilogue bound, an exposed load latency per tile would be the critical path)
+  int32_t res_mode;
   const float* bias;
   const __half* rowvec;
   int64_t rows_per_vec, ld_rowvec;
@@ -232,7 +238,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tfull_bar = bars + 4 * MAXS;          // [2]
   uint64_t* tempty_bar = bars + 4 * MAXS + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAXS + 4);
+  uint64_t* res_bar = bars + 4 * MAXS + 5;        // [1] residual tile landed in shared memory
   float* sbias = reinterpret_cast<float*>(aux + 512);  // [BLOCK_N]
+  // residual tile: the staging tile itself (mode 1) or the last STAGING_BYTES of the ring region (mode 2)
+  uint8_t* res_smem = (p.res_mode == 2) ? (smem + Cfg::RING_BYTES - Cfg::STAGING_BYTES) : staging;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -242,6 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
     if (tma_store) tma_prefetch_desc(&p.map_out);
+    if (tma_store && p.res_mode != 0) tma_prefetch_desc(&p.map_res);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < SA; ++s) {
@@ -256,6 +266,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], CL * (tma_store ? 8 : 4));
     mbar_init(&tempty_bar[1], CL * (tma_store ? 8 : 4));
+    mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -415,6 +426,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t l3 = r % p.box[3];
     r /= p.box[3];
     const uint32_t l4 = r;
+    uint32_t res_phase = 0;
+    // one thread: TMA-load the residual tile (64-column slabs, the layout the epilogue stores) and arm res_bar
+    auto issue_res_load = [&](int nb, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4) {
+      uint32_t bytes = 0;
+#pragma unroll
+      for (int sl = 0; sl < (OUT_TILE_N >= 64 ? OUT_TILE_N / 64 : 0); ++sl)
+        if (nb + sl * 64 < p.n_out) bytes += SLAB_BYTES;
+      mbar_expect_tx(res_bar, bytes);
+#pragma unroll
+      for (int sl = 0; sl < (OUT_TILE_N >= 64 ? OUT_TILE_N / 64 : 0); ++sl)
+        if (nb + sl * 64 < p.n_out)
+          tma_load_5d(&p.map_res, res_bar, res_smem + sl * SLAB_BYTES, nb + sl * 64, (int)c1, (int)c2, (int)c3, (int)c4);
+    };
     if (tma_store || half == 0) {
       uint32_t it = 0;
       for (uint32_t w = work0; w < num_work; w += work_stride, ++it) {
@@ -456,40 +480,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             }
             constexpr int COLS_PER_HALF = OUT_TILE_N / 2;
             constexpr int CHUNKS = COLS_PER_HALF / 32;
-            // residual operand: software-pipelined one chunk ahead, the first chunk BEFORE the wait for the
-            // accumulator, so the DRAM latency of these per-row 64-byte loads hides behind the main loop of the tile
-            // (short-K GEMMs spend one exposed latency per chunk otherwise)
-            uint4 rq_next[4];
-            auto load_res = [&](int c, uint4 (&dst)[4]) {
-              const int n0 = n_base + half * COLS_PER_HALF + c * 32;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                dst[g] = make_uint4(0, 0, 0, 0);
-                if (res != nullptr && n0 + g * 8 < p.n_out) dst[g] = ldg16(res + n0 + g * 8);
-              }
-            };
-            if constexpr (AUX) load_res(0, rq_next);
             if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if constexpr (AUX) {
+              // mode 1: the staging tile is free now -> fetch this tile's residual into it (in-place epilogue); the first
+              // tile of mode 2 is fetched here too (later ones are issued one tile ahead, right after the store below)
+              if (et == 0 && (p.res_mode == 1 || (p.res_mode == 2 && it == 0))) issue_res_load(n_base, t1, t2, t3, t4);
+            }
             epi_bar_sync();
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            if constexpr (AUX) {
+              if (p.res_mode != 0) {
+                mbar_wait(res_bar, res_phase);
+                res_phase ^= 1;
+              }
+            }
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
               const int col0 = half * COLS_PER_HALF + c * 32;  // column inside the output tile
               const int n0 = n_base + col0;
               const bool cols_ok = n0 < p.n_out;  // n_out % 8 == 0; groups of 8 checked below
               // issue the global loads first so their latency overlaps the TMEM load
-              uint4 rq[4], vq[4];
+              uint4 vq[4];
               if constexpr (AUX) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                  rq[g] = rq_next[g];
                   vq[g] = make_uint4(0, 0, 0, 0);
                   if (cols_ok && n0 + g * 8 < p.n_out) {
                     if (rv != nullptr) vq[g] = ldg16(rv + n0 + g * 8);
                   }
                 }
-                if (c + 1 < CHUNKS) load_res(c + 1, rq_next);
               }
               uint32_t a[32];
               tmem_ld_32x32(taddr + col0, a);
@@ -530,8 +550,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
                   }
-                  if (res != nullptr) fma_half8(x, p.out_scale, rq[g]);
-                  else if (p.out_scale != 1.0f) {
+                  if (p.res_mode != 0) {  // residual chunk of this row from shared memory (same swizzle as the store)
+                    const uint4 rq = *reinterpret_cast<const uint4*>(res_smem + slab * SLAB_BYTES + row * 128 +
+                                                                     (((chunk_base + g) ^ (row & 7)) << 4));
+                    fma_half8(x, p.out_scale, rq);
+                  } else if (p.out_scale != 1.0f) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] *= p.out_scale;
                   }
@@ -590,6 +613,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
               }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              if constexpr (AUX) {
+                // mode 2: every thread has consumed this tile's residual (barrier above) -> fetch the next tile's
+                if (p.res_mode == 2 && w + work_stride < num_work) {
+                  const uint32_t wn = w + work_stride;
+                  uint32_t i2 = (wn / p.n_tiles) * CL + cta_rank;
+                  const uint32_t u1 = (i2 % p.tiles[1]) * p.box[1];
+                  i2 /= p.tiles[1];
+                  const uint32_t u2 = (i2 % p.tiles[2]) * p.box[2];
+                  i2 /= p.tiles[2];
+                  const uint32_t u3 = (i2 % p.tiles[3]) * p.box[3];
+                  i2 /= p.tiles[3];
+                  issue_res_load((wn % p.n_tiles) * OUT_TILE_N, u1, u2, u3, i2 * p.box[4]);
+                }
+              }
             }
           }
         } else {
@@ -882,13 +919,28 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   UAV_REQUIRE(m_tiles * p.n_tiles < (1ull << 31), "igemm: too many tiles");
   p.num_tiles = (uint32_t)(m_tiles * p.n_tiles);
   p.num_pairs = (uint32_t)(((m_tiles + 1) / 2) * p.n_tiles);
+  // residual operand of the TMA-store epilogue (decided here because mode 2 takes its buffer out of the ring)
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool can_tma = out_tile_n >= 64 && e->out_dtype == UAV_F16 && p.n_out % 8 == 0 && e->ld_out % 8 == 0 &&
+                       aligned16(d.out) &&
+                       (e->residual == nullptr || (e->ld_res % 8 == 0 && aligned16(e->residual))) &&
+                       (e->rowvec == nullptr || (e->ld_rowvec % 8 == 0 && aligned16(e->rowvec)));
   {
     // ring split inside the fixed RING_BYTES region.  Convolutions re-read their activation tiles from L2
     // (9 taps) -> balanced rings.  Single-tap GEMMs stream activations from HBM (high latency) against L2-resident
     // weights -> deep A ring, shallow B ring.
     const int b_stage = block_n * BLOCK_K * 2 / (use_cluster ? 2 : 1);  // CTA pairs hold half a weight tile each
     const int staging = out_tile_n >= 64 ? (out_tile_n / 64) * SLAB_BYTES : 0;
-    const int ring = ((232448 - 1024 - staging - 2048) / 1024) * 1024;  // == IgemmCfg::RING_BYTES
+    int ring = ((232448 - 1024 - staging - 2048) / 1024) * 1024;  // == IgemmCfg::RING_BYTES
+    p.res_mode = 0;
+    if (can_tma && e->residual != nullptr) {
+      static const int res_knob = getenv("UAV_IGEMM_RES_MODE") ? atoi(getenv("UAV_IGEMM_RES_MODE")) : -1;
+      // single-tap GEMMs are HBM / epilogue bound: residual one tile ahead in its own buffer (if >= 3 stages remain)
+      const bool ahead = d.num_taps == 1 && (ring - staging) / (A_STAGE_BYTES + b_stage) >= 3;
+      p.res_mode = res_knob > 0 ? res_knob : (ahead ? 2 : 1);
+      if (p.res_mode == 2 && (ring - staging) / (A_STAGE_BYTES + b_stage) < 2) p.res_mode = 1;
+      if (p.res_mode == 2) ring -= staging;
+    }
     int sb = ring / (A_STAGE_BYTES + b_stage);  // balanced depth
     if (sb > 10) sb = 10;
     int sa = sb;
@@ -924,11 +976,6 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
 
   // TMA-store epilogue (smem-staged, fully coalesced, clips partial tiles) whenever the output
   // is an aligned fp16 tensor with at least 64-column tiles; otherwise per-row direct stores.
-  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  const bool can_tma = out_tile_n >= 64 && e->out_dtype == UAV_F16 && p.n_out % 8 == 0 &&
-                       p.ld_out % 8 == 0 && aligned16(d.out) &&
-                       (p.residual == nullptr || (p.ld_res % 8 == 0 && aligned16(p.residual))) &&
-                       (p.rowvec == nullptr || (p.ld_rowvec % 8 == 0 && aligned16(p.rowvec)));
   p.tma_store = can_tma ? 1 : 0;
   if (p.gn_partial != nullptr) {
     UAV_REQUIRE(can_tma && !geglu && d.out_strides[1] == 0,
@@ -954,6 +1001,17 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UAV_REQUIRE(r == CUDA_SUCCESS, "igemm: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+    if (p.res_mode != 0) {
+      uint64_t rs = (uint64_t)p.ld_res;
+      for (int i = 1; i < 5; ++i) {
+        strides[i - 1] = rs * 2;
+        rs *= d.out_dims[i];
+      }
+      r = encode(&p.map_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(p.residual), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      UAV_REQUIRE(r == CUDA_SUCCESS, "igemm: cuTensorMapEncodeTiled(residual) failed with %d", (int)r);
+    }
   }
 
   if (geglu) return launch_instance<256, true>(p, use_cluster, stream);
