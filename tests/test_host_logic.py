@@ -268,3 +268,37 @@ def test_synthetic_weights_match_the_oracle_rule():
         shapes = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"shapes_{kind}.json")))
         a, b = make_state_dict(shapes, 4321), seeded_state_dict(shapes, 4321)
         assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_pipeline_from_pretrained_local_layout(tmp_path):
+    """VideoUpscalePipeline.from_pretrained(local_dir, torch_dtype) — the first call of the reference CLI
+    (inference_upscale_a_video.py:101): text_encoder / low_res_scheduler / scheduler load from the shipped layout, a
+    checkpoint written by an older transformers (extra `position_ids` buffer) is accepted, anything else unexpected is not"""
+    import json
+    from upscale_a_video_b200 import CLIPTextConfig, CLIPTextModel, DDIMScheduler, DDPMScheduler, VideoUpscalePipeline
+    d = str(tmp_path)
+    for sub in ("text_encoder", "low_res_scheduler", "scheduler"):
+        os.makedirs(os.path.join(d, sub))
+    cfg = dict(vocab_size=1000, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+               max_position_embeddings=77, hidden_act="gelu", layer_norm_eps=1e-5)
+    json.dump(dict(cfg, model_type="clip_text_model", architectures=["CLIPTextModel"]), open(os.path.join(d, "text_encoder", "config.json"), "w"))
+    ref = CLIPTextModel(CLIPTextConfig(**cfg))
+    sd = dict(ref.state_dict())
+    sd["text_model.embeddings.position_ids"] = torch.arange(77)[None]
+    torch.save(sd, os.path.join(d, "text_encoder", "pytorch_model.bin"))
+    json.dump({"beta_schedule": "scaled_linear", "_class_name": "DDPMScheduler"}, open(os.path.join(d, "low_res_scheduler", "scheduler_config.json"), "w"))
+    json.dump({"beta_schedule": "scaled_linear", "prediction_type": "v_prediction", "steps_offset": 1, "clip_sample": False,
+               "set_alpha_to_one": False}, open(os.path.join(d, "scheduler", "scheduler_config.json"), "w"))
+    json.dump({"max_noise_level": 300}, open(os.path.join(d, "model_index.json"), "w"))
+    pipe = VideoUpscalePipeline.from_pretrained(d, torch_dtype=torch.float16)
+    assert isinstance(pipe.text_encoder, CLIPTextModel) and pipe.text_encoder.dtype == torch.float16
+    assert all(torch.equal(v.half(), pipe.text_encoder.state_dict()[k]) for k, v in ref.state_dict().items())
+    assert isinstance(pipe.low_res_scheduler, DDPMScheduler) and isinstance(pipe.scheduler, DDIMScheduler)
+    assert pipe.scheduler.config.prediction_type == "v_prediction" and pipe.config.max_noise_level == 300
+    assert pipe.vae is None and pipe.unet is None and pipe.tokenizer is None
+    sd["text_model.bogus.weight"] = torch.zeros(1)
+    torch.save(sd, os.path.join(d, "text_encoder", "pytorch_model.bin"))
+    with pytest.raises(RuntimeError):
+        VideoUpscalePipeline.from_pretrained(d)
+    with pytest.raises(EnvironmentError):
+        VideoUpscalePipeline.from_pretrained(os.path.join(d, "nope"))

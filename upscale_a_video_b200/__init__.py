@@ -1,7 +1,8 @@
 """uav_b200 — B200-native (sm_100a) implementation of the Upscale-A-Video diffusion sampling path.
 
 Public surface mirrors the reference (`/root/reference/models_video/`): `VideoUpscalePipeline`,
-`UNetVideoModel`, `AutoencoderKLVideo`, `DDIMScheduler`, `Propagation`.  The arithmetic runs in
+`UNetVideoModel`, `AutoencoderKLVideo`, `DDIMScheduler`, `Propagation`, `RAFT_bi` (models_video/RAFT/raft_bi.py) and the
+`CLIPTextModel` the pipeline holds as `text_encoder`.  The arithmetic runs in
 hand-written CUDA kernels behind a C ABI (`include/uav_b200.h`, `csrc/`); there is no CPU path.
 """
 __version__ = "0.1.0"
@@ -13,6 +14,11 @@ _LAZY = {
     "DDIMScheduler": "scheduling_ddim",
     "DDPMScheduler": "scheduling_ddim",
     "Propagation": "propagation_module",
+    "RAFT": "raft",
+    "RAFT_bi": "raft",
+    "initialize_RAFT": "raft",
+    "CLIPTextModel": "clip_text",
+    "CLIPTextConfig": "clip_text",
 }
 
 

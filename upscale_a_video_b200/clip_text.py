@@ -89,6 +89,33 @@ class CLIPTextModel(PackedModule):
     def device(self):
         return next(self.parameters()).device
 
+    @classmethod
+    def from_pretrained(cls, path: str, torch_dtype=None, **_):
+        """`transformers.CLIPTextModel.from_pretrained(dir)` for a local directory: `config.json` (a `text_config` block is
+        unwrapped) + `model.safetensors` or `pytorch_model.bin` with transformers' own key names"""
+        import json
+        import os
+        cfg = json.load(open(os.path.join(path, "config.json")))
+        cfg = cfg.get("text_config", cfg)
+        keys = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                "max_position_embeddings", "hidden_act", "layer_norm_eps")
+        model = cls(CLIPTextConfig(**{k: cfg[k] for k in keys if k in cfg}))
+        st = os.path.join(path, "model.safetensors")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+        own = model.state_dict()
+        # checkpoints written by other transformers versions carry buffers we do not hold (position_ids) — drop those only
+        extra = [k for k in sd if k not in own]
+        if any(not k.endswith("position_ids") for k in extra):
+            raise RuntimeError(f"unexpected keys in the text-encoder checkpoint: {[k for k in extra if not k.endswith('position_ids')][:5]}")
+        model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)
+        if torch_dtype is not None:
+            model = model.to(torch_dtype)
+        return model.eval()
+
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, **_):
         """returns (last_hidden_state (b, n, hidden) in the model dtype, None): index [0] like the reference does"""

@@ -519,10 +519,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 tmem_ld_32x32(taddr + BLOCK_N / 2 + col0, gt);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float hh = __uint_as_float(a[j]) + sbias[col0 + j];
-                  const float gg = __uint_as_float(gt[j]) + sbias[OUT_TILE_N + col0 + j];
-                  v[j] = hh * gelu_erf_f(gg);
+                for (int j4 = 0; j4 < 8; ++j4) {  // bias tiles as 128-bit broadcast loads (2 scalar LDS per output before)
+                  const float4 bh = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
+                  const float4 bg = *reinterpret_cast<const float4*>(sbias + OUT_TILE_N + col0 + j4 * 4);
+                  v[j4 * 4 + 0] = (__uint_as_float(a[j4 * 4 + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 0]) + bg.x);
+                  v[j4 * 4 + 1] = (__uint_as_float(a[j4 * 4 + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 1]) + bg.y);
+                  v[j4 * 4 + 2] = (__uint_as_float(a[j4 * 4 + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 2]) + bg.z);
+                  v[j4 * 4 + 3] = (__uint_as_float(a[j4 * 4 + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 3]) + bg.w);
                 }
               } else {
                 tmem_ld_wait();

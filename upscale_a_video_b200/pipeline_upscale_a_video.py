@@ -46,6 +46,45 @@ class VideoUpscalePipeline(ConfigMixin):
         self.register_to_config(max_noise_level=max_noise_level)
         self.process_group = None  # torch.distributed group used for window / chunk sharding (None = default)
 
+    # ------------------------------------------------------------------ loading (inference_upscale_a_video.py:101)
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype=None, **_):
+        """`DiffusionPipeline.from_pretrained(local_dir, torch_dtype=...)` for the layout the reference ships
+        (README.md:78-101): `text_encoder/` (CLIP text model: config.json + weights) -> the B200 `CLIPTextModel`,
+        `tokenizer/` -> `transformers.CLIPTokenizer` (host-side string processing, not on the GPU path),
+        `low_res_scheduler/scheduler_config.json` -> `DDPMScheduler`, and — when present — `scheduler/`, `vae/`, `unet/`
+        (the reference CLI overwrites these three right after, lines 104-121).  Components that are absent stay None."""
+        import json
+        import os
+        from .clip_text import CLIPTextModel
+        from .scheduling_ddim import DDIMScheduler, DDPMScheduler
+        root = pretrained_model_name_or_path
+        if not os.path.isdir(root):
+            raise EnvironmentError(f"{root} is not a local directory (there is no hub access: pass the downloaded folder)")
+
+        def sub(*names):
+            q = os.path.join(root, *names)
+            return q if os.path.exists(q) else None
+
+        text_encoder = tokenizer = low_res = sched = None
+        if sub("text_encoder", "config.json"):
+            text_encoder = CLIPTextModel.from_pretrained(sub("text_encoder"), torch_dtype=torch_dtype)
+        if sub("tokenizer"):
+            try:
+                from transformers import CLIPTokenizer
+            except ImportError as e:  # pragma: no cover
+                raise ImportError("the tokenizer of the text prompt needs `transformers` (CLIPTokenizer)") from e
+            tokenizer = CLIPTokenizer.from_pretrained(sub("tokenizer"))
+        if sub("low_res_scheduler", "scheduler_config.json"):
+            low_res = DDPMScheduler.from_config(json.load(open(sub("low_res_scheduler", "scheduler_config.json"))))
+        if sub("scheduler", "scheduler_config.json"):
+            sched = DDIMScheduler.from_config(json.load(open(sub("scheduler", "scheduler_config.json"))))
+        max_noise_level = 350
+        if sub("model_index.json"):
+            max_noise_level = json.load(open(sub("model_index.json"))).get("max_noise_level", 350)
+        return cls(text_encoder=text_encoder, tokenizer=tokenizer, low_res_scheduler=low_res, scheduler=sched, vae=None,
+                   unet=None, propagator=None, max_noise_level=max_noise_level)
+
     # ------------------------------------------------------------------ plumbing
     def to(self, device):
         for name in ("vae", "text_encoder", "unet", "propagator"):
