@@ -168,12 +168,19 @@ typedef struct {
   int64_t blocks;
   int64_t C;           /* channels of this source, % 8 == 0 */
   int64_t slabs;
+  /* the source tensor itself, for a concatenation that is never materialised (all sources then carry one; x of the call
+   * is ignored): fp16 [slab][pixels][ld]; slab_stride = elements between slabs, 0 when every n reads the same rows */
+  const void* x;
+  int64_t ld;
+  int64_t slab_stride;
 } uav_gn_source_t;
 
 /* uav_groupnorm_silu without the statistics read pass: x is the channel concatenation (in order) of up to 4 tensors
  * whose producers emitted their statistics blocks (the torch.cat of unet_blocks.py:573,645 followed by resnet.py:267).
  * (C / groups) % 8 == 0.  Two launches (fp64 fixed-order reduction of the blocks, apply) instead of three, and
- * 2 instead of 3 element passes over x.  workspace: uav_groupnorm_workspace_bytes. */
+ * 2 instead of 3 element passes over x.  When the sources carry their own tensors (source.x), the concatenation is
+ * never built: the apply pass runs once per source and writes the normalised, DENSE [.., C] tensor y that the following
+ * convolution reads (x / ld_in of the call are then unused).  workspace: uav_groupnorm_workspace_bytes. */
 uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, int64_t pixels, int64_t C,
                                               int64_t ld_in, int groups, const float* gamma, const float* beta,
                                               float eps, int silu, void* y, int64_t ld_out,

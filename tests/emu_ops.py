@@ -35,19 +35,49 @@ def _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, ou
     return v
 
 
-def _finish(v, lead_shape, out, out_dtype):
+GN_FUSED_STATS = True  # mirrors ops.GN_FUSED_STATS (read by layers.new_cat_slot)
+
+
+class EmuStats:
+    """stand-in for ops.GnStats: marks a tensor whose producer "emitted" GroupNorm statistics, so that the host logic
+    around them (virtual concat, slot allocation) runs on the CPU; the emulated GroupNorm recomputes its statistics"""
+
+    def __init__(self, C, batch):
+        self.C, self.batch = C, batch
+
+    def slabs_for(self, n_outer, batch):
+        return n_outer if self.batch == batch else (1 if self.batch == 1 and n_outer == batch else 0)
+
+
+def _finish(v, lead_shape, out, out_dtype, gn_stats=False):
     v = v.reshape(*lead_shape, v.shape[-1])
     if out is None:
-        return v.to(out_dtype)
-    out.copy_(v)
+        out = v.to(out_dtype)
+    else:
+        out.copy_(v)
+    if gn_stats and out.dtype == torch.float16 and out.shape[-1] >= 64 and out.shape[-1] % 8 == 0:
+        out.uav_gn = [EmuStats(out.shape[-1], out.shape[0] if out.dim() > 2 else 1)]
     return out
+
+
+def group_norm_cat(parts, gamma, beta, groups, eps, *, silu, n_outer):
+    B = max(p.shape[0] for p in parts)
+    C = sum(p.shape[-1] for p in parts)
+    if (C // groups) % 8 or n_outer != B:
+        return None
+    for p in parts:
+        st = getattr(p, "uav_gn", None)
+        if not st or len(st) != 1 or not st[0].slabs_for(n_outer, B):
+            return None
+    cat = torch.cat([p.expand(B, *p.shape[1:]) for p in parts], dim=-1)
+    return group_norm(cat, gamma, beta, groups, eps, silu=silu, n_outer=n_outer)
 
 
 def linear(a, w, bias=None, *, out=None, residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16,
            out_scale=1.0, gn_stats=False):
     acc = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
     v = _epilogue(acc, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, out_scale)
-    return _finish(v, a.shape[:-1], out, out_dtype)
+    return _finish(v, a.shape[:-1], out, out_dtype, gn_stats and act != ACT_GEGLU)
 
 
 def _conv_nhwc(x4, w, stride, pads):
@@ -69,7 +99,7 @@ def conv2d(x, w, bias=None, *, stride=1, pad_mode=0, out=None, residual=None, ro
     else:  # F.pad (0, 1, 0, 1) then no padding
         y = _conv_nhwc(x4, w, 2, (0, 1, 0, 1))
     v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, out_scale)
-    return _finish(v, (*lead, y.shape[1], y.shape[2]), out, out_dtype)
+    return _finish(v, (*lead, y.shape[1], y.shape[2]), out, out_dtype, gn_stats)
 
 
 def collapse_upsample_filter(w):
@@ -105,14 +135,14 @@ def conv_temporal(x, w, bias=None, *, out=None, residual=None, rowvec=None, rows
     xp = F.pad(x.float().permute(0, 4, 1, 2, 3), (0, 0, 0, 0, k // 2, k // 2))
     y = F.conv3d(xp, w.float().permute(0, 2, 1)[:, :, :, None, None]).permute(0, 2, 3, 4, 1)
     v = _epilogue(y, bias, rowvec, rows_per_vec, residual, act, out, out_dtype, out_scale)
-    return _finish(v, (B, T, H, W), out, out_dtype)
+    return _finish(v, (B, T, H, W), out, out_dtype, gn_stats)
 
 
 def conv3d(x, w, bias=None, *, out=None, residual=None, act=ACT_NONE, out_dtype=torch.float16, out_scale=1.0, gn_stats=False):
     B, T, H, W, Cin = x.shape
     y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float().permute(0, 4, 1, 2, 3), padding=1).permute(0, 2, 3, 4, 1)
     v = _epilogue(y, bias, None, 0, residual, act, out, out_dtype, out_scale)
-    return _finish(v, (B, T, H, W), out, out_dtype)
+    return _finish(v, (B, T, H, W), out, out_dtype, gn_stats)
 
 
 def group_norm(x, gamma, beta, groups, eps, *, silu, n_outer, out=None, stats=None, batch=None):
@@ -188,6 +218,16 @@ def concat_channels(a, b):
 
 
 def repeat_batch(x, n):
+    return _carry(_repeat_batch(x, n), x)
+
+
+def _carry(dst, src):
+    if getattr(src, "uav_gn", None):
+        dst.uav_gn = src.uav_gn
+    return dst
+
+
+def _repeat_batch(x, n):
     return x.repeat(n, *([1] * (x.dim() - 1)))
 
 

@@ -325,3 +325,24 @@ def test_residual_tile_through_tma(M, K, N):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wc.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) + r.float()
     _close(buf[..., 64:], ref, 576, "conv+res -> slice")
     assert buf[..., :64].abs().max().item() == 0
+
+
+def test_groupnorm_of_a_concat_that_is_never_built():
+    """ops.group_norm_cat: GroupNorm(cat([x, skip])) -> dense tensor, the two inputs read in place (one apply launch per
+    part), statistics from their producers; a batch-1 skip serves both batch items; groups straddle the boundary"""
+    torch.manual_seed(5)
+    B, T, H, W = 2, 3, 12, 20
+    for cx, cs, skip_b in ((1024, 512, 1), (512, 256, 2), (256, 256, 1)):
+        x = ops.conv2d(_rand(B, T, H, W, 64), _rand(cx, 3, 3, 64, scale=0.05), None, gn_stats=True)
+        skip = ops.linear(_rand(skip_b, T, H * W, 128), _rand(cs, 128, scale=0.1), torch.randn(cs, device=DEV), gn_stats=True)
+        st = skip.uav_gn
+        skip = skip.view(skip_b, T, H, W, cs)
+        skip.uav_gn = st  # a reshaped view keeps its producer's statistics (layers._carry_gn)
+        C = cx + cs
+        gamma, beta = torch.randn(C, device=DEV) * 0.2 + 1, torch.randn(C, device=DEV) * 0.1
+        got = ops.group_norm_cat([x, skip], gamma, beta, 32, 1e-5, silu=True, n_outer=B)
+        assert got is not None and tuple(got.shape) == (B, T, H, W, C) and got.is_contiguous()
+        cat = torch.cat([x, skip.expand(B, -1, -1, -1, -1)], dim=-1)
+        _check(got, _gn_ref(cat, gamma, beta, 32, 1e-5, True, B), atol=4e-3)
+    # a part without statistics -> None (the caller materialises the concat)
+    assert ops.group_norm_cat([x, _rand(B, T, H, W, 256)], gamma, beta, 32, 1e-5, silu=True, n_outer=B) is None

@@ -43,7 +43,8 @@ class Epilogue(C.Structure):
 
 class GnSource(C.Structure):
     """uav_gn_source_t"""
-    _fields_ = [("partial", C.c_void_p), ("blocks", C.c_int64), ("C", C.c_int64), ("slabs", C.c_int64)]
+    _fields_ = [("partial", C.c_void_p), ("blocks", C.c_int64), ("C", C.c_int64), ("slabs", C.c_int64),
+                ("x", C.c_void_p), ("ld", C.c_int64), ("slab_stride", C.c_int64)]
 
 
 I64, I32, P, F32 = C.c_int64, C.c_int, C.c_void_p, C.c_float

@@ -235,10 +235,13 @@ __global__ void __launch_bounds__(GN_THREADS)
     gn_apply_vec_kernel(const __half* __restrict__ x, int64_t pixels, int C, int64_t ld_in, int G,
                         const double* __restrict__ sums, int nsplit, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, int silu, __half* __restrict__ y,
-                        int64_t ld_out) {
+                        int64_t ld_out, int c_total, int chan_off, int64_t x_slab_stride) {
+  // C channels of THIS launch = channels [chan_off, chan_off + C) of a c_total-channel GroupNorm whose input is the
+  // channel concatenation of several tensors (x_slab_stride: elements between the statistics slabs of this source, 0 when
+  // the same rows serve every n); the plain case is c_total == C, chan_off == 0, x_slab_stride == pixels * ld_in
   const int n = blockIdx.y;
   const int octs = C >> 3;
-  const int cpg = C / G;
+  const int cpg = c_total / G;
   const int pix_per_iter = GN_THREADS / octs;
   const int my_pix = threadIdx.x / octs;
   const int oct = threadIdx.x % octs;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(GN_THREADS)
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = oct * 8 + j;
+    const int c = chan_off + oct * 8 + j;
     const int g = c / cpg;
     double s = 0.0, q = 0.0;
     for (int k = 0; k < nsplit; ++k) {  // fixed order: the statistics may arrive as `nsplit` partial sums per group
@@ -261,8 +264,8 @@ __global__ void __launch_bounds__(GN_THREADS)
     sc[j] = gamma[c] * rstd;
     sh[j] = beta[c] - static_cast<float>(mean) * sc[j];
   }
-  const __half* xn = x + static_cast<int64_t>(n) * pixels * ld_in + oct * 8;
-  __half* yn = y + static_cast<int64_t>(n) * pixels * ld_out + oct * 8;
+  const __half* xn = x + static_cast<int64_t>(n) * x_slab_stride + oct * 8;
+  __half* yn = y + static_cast<int64_t>(n) * pixels * ld_out + chan_off + oct * 8;
   auto one = [&](int64_t p, const uint4& v) {
     const __half2* h = reinterpret_cast<const __half2*>(&v);
     uint4 o;
@@ -517,7 +520,7 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
       if (gxa < 1) gxa = 1;
       gn_apply_vec_kernel<<<dim3((unsigned)gxa, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
           reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums, 1, gamma, beta, eps, silu,
-          reinterpret_cast<__half*>(y), ld_out);
+          reinterpret_cast<__half*>(y), ld_out, (int)C, 0, pixels * ld_in);
     } else {
       const int64_t work = pixels * C;
       int64_t want = (sms * 16 + n_outer - 1) / n_outer;
@@ -541,14 +544,15 @@ uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, in
                                               const uav_gn_source_t* sources, int n_sources, void* workspace,
                                               size_t workspace_bytes, uav_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  UAV_REQUIRE(x && y && gamma && beta && workspace && sources, "uav_groupnorm_silu_from_partials: null pointer");
+  UAV_REQUIRE(y && gamma && beta && workspace && sources, "uav_groupnorm_silu_from_partials: null pointer");
+  UAV_REQUIRE(x != nullptr || sources[0].x != nullptr, "uav_groupnorm_silu_from_partials: no input tensor");
   UAV_REQUIRE(n_outer > 0 && n_outer <= 65535 && pixels > 0 && C > 0 && C <= 2048 && groups > 0 && C % groups == 0 &&
-                  ld_in >= C && ld_out >= C,
+                  ld_out >= C,
               "uav_groupnorm_silu_from_partials: bad shape (C=%lld groups=%d)", (long long)C, groups);
   const int cpg = (int)(C / groups);
   UAV_REQUIRE(cpg % 8 == 0, "uav_groupnorm_silu_from_partials: channels per group (%d) must be a multiple of 8", cpg);
-  UAV_REQUIRE(C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+  UAV_REQUIRE(C % 8 == 0 && (x == nullptr || (ld_in % 8 == 0 && ld_in >= C)) && ld_out % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
               "uav_groupnorm_silu_from_partials: tensors must be 16-byte aligned with ld %% 8 == 0");
   UAV_REQUIRE(n_sources >= 1 && n_sources <= 4, "uav_groupnorm_silu_from_partials: 1..4 sources");
   UAV_REQUIRE(workspace_bytes >= uav_groupnorm_workspace_bytes(n_outer, groups),
@@ -584,17 +588,33 @@ uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, in
   double* sums = reinterpret_cast<double*>(workspace);  // [n][g][S][2] <= the stats-kernel partial area
   gn_reduce_partials_kernel<<<dim3((unsigned)groups, (unsigned)n_outer, (unsigned)S), 256, 0, stream>>>(prm, sums);
   UAV_CHECK_CUDA(cudaGetLastError());
-  const int octs = (int)(C / 8);
-  const int pix_per_iter = GN_THREADS / octs;
-  int64_t want = ((int64_t)num_sms() * 16 + n_outer - 1) / n_outer;
-  int64_t maxb = (pixels + pix_per_iter * 4 - 1) / (pix_per_iter * 4);
-  int64_t gxa = want < maxb ? want : maxb;
-  if (gxa < 1) gxa = 1;
-  gn_apply_vec_kernel<<<dim3((unsigned)gxa, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
-      reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, sums, (int)S, gamma, beta, eps, silu,
-      reinterpret_cast<__half*>(y), ld_out);
-  UAV_CHECK_CUDA(cudaGetLastError());
-  g_launches.fetch_add(2, std::memory_order_relaxed);
+  // apply: one launch over x, or — when the sources carry their own tensors (a concat that was never materialised) — one
+  // launch per source, each writing its channel range of the dense output
+  const bool per_source = sources[0].x != nullptr;
+  int launches = 1;
+  int chan = 0;
+  for (int i = 0; i < (per_source ? n_sources : 1); ++i) {
+    const int64_t Cs = per_source ? sources[i].C : C;
+    const __half* xs = reinterpret_cast<const __half*>(per_source ? sources[i].x : x);
+    const int64_t lds = per_source ? sources[i].ld : ld_in;
+    const int64_t slab_stride = per_source ? sources[i].slab_stride : pixels * ld_in;
+    if (per_source)
+      UAV_REQUIRE(xs != nullptr && lds >= Cs && lds % 8 == 0 && (reinterpret_cast<uintptr_t>(xs) & 15) == 0 && Cs <= 2048,
+                  "uav_groupnorm_silu_from_partials: bad tensor of source %d", i);
+    const int octs = (int)(Cs / 8);
+    const int pix_per_iter = GN_THREADS / octs;
+    int64_t want = ((int64_t)num_sms() * 16 + n_outer - 1) / n_outer;
+    int64_t maxb = (pixels + pix_per_iter * 4 - 1) / (pix_per_iter * 4);
+    int64_t gxa = want < maxb ? want : maxb;
+    if (gxa < 1) gxa = 1;
+    gn_apply_vec_kernel<<<dim3((unsigned)gxa, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
+        xs, pixels, (int)Cs, lds, groups, sums, (int)S, gamma, beta, eps, silu, reinterpret_cast<__half*>(y), ld_out, (int)C,
+        chan, slab_stride);
+    UAV_CHECK_CUDA(cudaGetLastError());
+    chan += (int)Cs;
+    launches = 1 + i + 1;
+  }
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
   return UAV_OK;
 }
 

@@ -197,6 +197,13 @@ def _gn(c: Ctx, norm: nn.GroupNorm, x, silu: bool, n_outer: int, stream_scale: f
                           batch=x.shape[0])
 
 
+def _split_1x1(conv, cx: int):
+    """1x1 conv weight (Cout, Cx + Cs, 1, 1) -> ([Cout][Cx], [Cout][Cs]) fp16 K-major blocks + fp32 bias"""
+    w = conv.weight.detach()[:, :, 0, 0]
+    return (w[:, :cx].to(torch.float16).contiguous(), w[:, cx:].to(torch.float16).contiguous(),
+            None if conv.bias is None else conv.bias.detach().float().contiguous())
+
+
 def _carry_gn(dst, src):
     """a reshaped view of a produced tensor keeps the producer's GroupNorm statistics and its concat-buffer membership"""
     for name in ("uav_gn", "uav_cat"):
@@ -213,10 +220,19 @@ def _carry_gn(dst, src):
 INPLACE_CONCAT = os.environ.get("UAV_INPLACE_CONCAT", "1") != "0"
 
 
-def new_cat_slot(skip, cx: int, batch: int):
+# ... and where both halves carry the GroupNorm statistics of their producers, the concat is never built at all
+# (ResnetBlock3D.forward_cat): norm1 normalises the two tensors straight into ONE dense tensor (ops.group_norm_cat) and the
+# 1x1 conv_shortcut over the concat is split into its two column blocks.  UAV_VIRTUAL_CONCAT=0 disables it.
+VIRTUAL_CONCAT = os.environ.get("UAV_VIRTUAL_CONCAT", "1") != "0"
+
+
+def new_cat_slot(skip, cx: int, batch: int, producer_has_stats: bool = False):
     """-> the head slice (batch, t, h, w, cx) of a fresh concat buffer whose tail already holds `skip`; the producer of
-    the main branch writes into it and `cat_with_skip` later returns the whole buffer"""
+    the main branch writes into it and `cat_with_skip` later returns the whole buffer.  None (plain allocation by the
+    producer) when the concat will not be materialised at all."""
     if not INPLACE_CONCAT:
+        return None
+    if VIRTUAL_CONCAT and ops.GN_FUSED_STATS and producer_has_stats and getattr(skip, "uav_gn", None):
         return None
     cs = skip.shape[-1]
     buf = torch.empty(batch, *skip.shape[1:-1], cx + cs, dtype=skip.dtype, device=skip.device)
@@ -261,6 +277,33 @@ class ResnetBlock3D(nn.Module):
 
     def _convs(self, c, h, which, **epi):
         return getattr(self, which).run(c, h, **epi)
+
+    def forward_cat(self, c: Ctx, x, skip, out=None):
+        """forward(torch.cat([x, skip], channel)) (unet_blocks.py:573,645) without building the concatenation when both
+        tensors carry their producers' GroupNorm statistics; otherwise through the (in-place) concat buffer"""
+        h = None
+        if (VIRTUAL_CONCAT and self.conv_shortcut is not None and isinstance(self.conv_shortcut, InflatedConv3d)
+                and getattr(x, "uav_cat", None) is None):
+            g, b = c.pk.affine(self.norm1)
+            h = ops.group_norm_cat([x, skip], g, b, self.norm1.num_groups, self.norm1.eps, silu=True, n_outer=x.shape[0])
+        if h is None:
+            return self.forward(c, cat_with_skip(x, skip), out=out)
+        B = x.shape[0]
+        thw = x.shape[1] * x.shape[2] * x.shape[3]
+        temb = c.temb(self) if self.time_emb_proj is not None else None
+        h = self._convs(c, h, "conv1", rowvec=temb, rows_per_vec=thw, gn_stats=True)
+        h = _gn(c, self.norm2, h, True, B)
+        # conv_shortcut(cat) = Wx x + Ws skip + b: the skip half first (once, if the skip is shared by the batch items)
+        cx = x.shape[-1]
+        wx, ws, bias = c.pk.tensor(f"shortcut_split{id(self.conv_shortcut)}_{cx}", lambda: _split_1x1(self.conv_shortcut, cx))
+        s1 = ops.linear(skip, ws, None)
+        if skip.shape[0] == B:
+            xs = ops.linear(x, wx, bias, residual=s1)
+        else:
+            xs = torch.empty(*x.shape[:-1], wx.shape[0], dtype=torch.float16, device=x.device)
+            for n in range(B):
+                ops.linear(x[n:n + 1], wx, bias, residual=s1, out=xs[n:n + 1])
+        return self._convs(c, h, "conv2", residual=xs, gn_stats=True, out=out)
 
     def forward(self, c: Ctx, x, stream_scale: float = 1.0, out=None):
         """`stream_scale` (VAE decoder): x and the result are stream_scale x the reference's residual stream;
@@ -360,7 +403,7 @@ class Downsample3D(nn.Module):
 
     def forward(self, c: Ctx, x):
         assert x.shape[-1] == self.channels
-        return self.conv.run(c, x)
+        return self.conv.run(c, x, gn_stats=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -670,15 +713,16 @@ class UpBlock3D(nn.Module):
         n = len(self.resnets)
         B = x.shape[0]
         for i, r in enumerate(self.resnets):
-            x = cat_with_skip(x, skips[-1 - i])
             last = i == n - 1
             # the main branch of the next concat is produced by this stage's last layer: let it store there directly
-            nxt = (out if self.upsamplers is None else None) if last else new_cat_slot(skips[-2 - i], r.out_channels, B)
+            # (unless that concat will not be materialised at all: both halves carry GroupNorm statistics)
+            nxt = (out if self.upsamplers is None else None) if last else \
+                new_cat_slot(skips[-2 - i], r.out_channels, B, GN_STATS_LINEAR if self.attentions is not None else True)
             if self.attentions is not None:
-                x = r(c, x)
+                x = r.forward_cat(c, x, skips[-1 - i])
                 x = self.attentions[i](c, x, out=nxt)
             else:
-                x = r(c, x, out=nxt)
+                x = r.forward_cat(c, x, skips[-1 - i], out=nxt)
         if self.upsamplers is not None:
             x = self.upsamplers[0](c, x, upsample_size, out=out)
         return x

@@ -345,6 +345,47 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     return out
 
 
+def group_norm_cat(parts, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *, silu: bool, n_outer: int):
+    """GroupNorm(+SiLU) of torch.cat(parts, channel) WITHOUT building the concatenation (unet_blocks.py:573,645 followed by
+    resnet.py:267): every part carries the statistics blocks its producer emitted; one reduction over all of them, then one
+    apply launch per part writing its channel range of the dense result.  A part with batch 1 (computed once for both
+    classifier-free-guidance halves) serves every batch item.  Returns None when a part cannot serve (no statistics,
+    misaligned slabs): the caller then materialises the concat."""
+    B = max(p.shape[0] for p in parts)
+    C = sum(p.shape[-1] for p in parts)
+    if (C // groups) % 8 or len(parts) > 4 or n_outer != B:
+        return None
+    lead = None
+    srcs = (_lib.GnSource * len(parts))()
+    for i, p in enumerate(parts):
+        st = getattr(p, "uav_gn", None)
+        if not st or len(st) != 1 or st[0].C != p.shape[-1] or p.dtype != torch.float16 or p.shape[0] not in (1, B):
+            return None
+        sl = st[0].slabs_for(n_outer, B)
+        if not sl:
+            return None
+        if lead is None:
+            lead = tuple(p.shape[1:-1])
+        if tuple(p.shape[1:-1]) != lead:
+            return None
+        ld = _pixel_ld(p)
+        pix = p.numel() // p.shape[-1] // p.shape[0]
+        srcs[i].partial, srcs[i].blocks, srcs[i].C, srcs[i].slabs = st[0].partial.data_ptr(), st[0].blocks, st[0].C, sl
+        srcs[i].x, srcs[i].ld, srcs[i].slab_stride = p.data_ptr(), ld, (pix * ld if p.shape[0] == B and B > 1 else 0)
+        if B == 1:
+            srcs[i].slab_stride = 0
+    out = torch.empty(B, *lead, C, dtype=torch.float16, device=parts[0].device)
+    pixels = out.numel() // C // n_outer
+    lib = _lib.load()
+    ws = _gn_workspace(out.device, lib.uav_groupnorm_workspace_bytes(n_outer, groups))
+    with _timed("groupnorm", 0.0, 2.0 * 2 * out.numel(), f"gn(virtual concat) {out.numel() // C}px C{C}"):
+        _lib.check(lib.uav_groupnorm_silu_from_partials(None, n_outer, pixels, C, C, groups, gamma.data_ptr(), beta.data_ptr(),
+                                                        eps, 1 if silu else 0, out.data_ptr(), C, srcs, len(parts),
+                                                        ws.data_ptr(), ws.numel(), _stream()),
+                   "uav_groupnorm_silu_from_partials")
+    return out
+
+
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, out=None):
     assert x.dtype == torch.float16 and gamma.dtype == torch.float32
     C = x.shape[-1]

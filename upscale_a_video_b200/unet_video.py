@@ -29,6 +29,7 @@ from ._lib import UavError
 from .layers import (CrossAttention, CrossAttnDownBlock3D, CrossAttnUpBlock3D, Ctx, DownBlock3D, EmptyTemporalModule3D,
                      InflatedConv3d, PackedModule, ResnetBlock3D, RotaryEmbedding, TemporalModule3D,
                      UNetMidBlock3DCrossAttn, UpBlock3D, _gn, new_cat_slot)
+from . import layers as _layers
 
 
 @dataclass
@@ -281,16 +282,16 @@ class UNetVideoModel(PackedModule, ConfigMixin):
             _tap(f"down_temp{i}", x)
         # every up-block resnet consumes torch.cat([x, skip]): the layer that produces x stores straight into the head of the
         # concat buffer (layers.new_cat_slot), so only the skip half is ever copied
-        def first_slot(i, cx, size_hw=None):
+        def first_slot(i, cx, size_hw=None, producer_has_stats=False):
             """head slice of the concat buffer of up block i's first resnet (None: plain allocation by the producer)"""
             skip = skips[-1]
             if size_hw is not None and tuple(skip.shape[2:4]) != tuple(size_hw):
                 return None
-            return new_cat_slot(skip, cx, B)
+            return new_cat_slot(skip, cx, B, producer_has_stats)
 
         mid_empty = isinstance(self.mid_temp_block, EmptyTemporalModule3D)
         c_mid = cfg.block_out_channels[-1]
-        slot = first_slot(0, c_mid, x.shape[2:4])
+        slot = first_slot(0, c_mid, x.shape[2:4], True if mid_empty else _layers.GN_STATS_LINEAR)
         x = self.mid_block(c, x, out=slot if mid_empty else None)
         _tap("mid", x)
         x = self.mid_temp_block(c, x, out=None if mid_empty else slot)
@@ -304,7 +305,10 @@ class UNetVideoModel(PackedModule, ConfigMixin):
             slot = None
             if not final:
                 hw = tuple(up_size[1:]) if up_size is not None else (2 * x.shape[2], 2 * x.shape[3])
-                slot = first_slot(i + 1, blk.resnets[-1].out_channels, hw)
+                # producer of the next block's main branch: the temporal module's shift_conv (statistics if Linear producers
+                # emit them) or, without a temporal module, the upsampler conv (its four phase launches emit none)
+                slot = first_slot(i + 1, blk.resnets[-1].out_channels, hw,
+                                  False if t_empty else _layers.GN_STATS_LINEAR)
             x = blk(c, x, res, up_size, out=slot if t_empty else None)
             _tap(f"up{i}", x)
             x = tmod(c, x, out=None if t_empty else slot)
