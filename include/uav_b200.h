@@ -187,6 +187,45 @@ uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, in
                                               const uav_gn_source_t* sources, int n_sources, void* workspace,
                                               size_t workspace_bytes, uav_stream_t stream);
 
+/* Only the per-(slab, channel) affine of a GroupNorm, for a consumer that applies it itself (uav_conv_out_fused):
+ * affine fp32 [n_outer][C][2] = {gamma * rstd, beta - mean * gamma * rstd}.  Statistics from the producers' blocks
+ * (n_sources > 0; x may be NULL) or from a read pass over x (n_sources == 0). */
+uav_status_t uav_groupnorm_affine(const void* x, int64_t n_outer, int64_t pixels, int64_t C, int64_t ld_in, int groups,
+                                  const float* gamma, const float* beta, float eps, const uav_gn_source_t* sources,
+                                  int n_sources, float* affine, void* workspace, size_t workspace_bytes,
+                                  uav_stream_t stream);
+
+/* The tail of UNetVideoModel.forward in one HBM-bound kernel (unet_video.py:567-569):
+ *   out = conv_out(SiLU(GroupNorm(x)))    3x3, zero padding 1, C = 256 -> Cout <= 5 channels,
+ * x: fp16 [B][T][H][W][ld] (raw, before conv_norm_out), affine: the GroupNorm's fp32 [B][C][2] table from
+ * uav_groupnorm_affine, w: fp16 [Cout][3][3][C], out: the reference's planar "b c t h w" tensor [B][Cout][T][H][W] in
+ * out_dtype.  Reads x once (no normalised copy of the 256-channel tensor is ever written), replaces GroupNorm apply +
+ * InflatedConv3d (resnet.py:94-101) + the rearrange back to b c t h w. */
+uav_status_t uav_conv_out_fused(const void* x, int64_t B, int64_t T, int64_t H, int64_t W, int64_t C, int64_t ld,
+                                const float* affine, const void* w, const float* bias, int64_t Cout, void* out,
+                                int out_dtype, uav_stream_t stream);
+
+/* ... and the same kernel with the sampler arithmetic of the step in its epilogue (BASELINE north_star: "DDIM step +
+ * classifier-free-guidance add fused into the UNet epilogue"): the two batch items of x are the unconditional / text halves
+ * of ONE clip; per output element, with torch's per-op fp16 rounding (bit-identical to uav_cfg_combine followed by
+ * uav_ddim_step_v0 on the fp16 output of uav_conv_out_fused):
+ *   noise_pred = u + g * (c - u)                                   (pipeline_upscale_a_video.py:644-645)
+ *   pred_original_sample = DDIMScheduler.step_v0(noise_pred, sample) (scheduling_ddim.py:383-433)
+ * All three tensors are fp16 (1, Cout, T, H, W) in the reference layout.  x: fp16 [2][T][H][W][ld]. */
+typedef struct {
+  float guidance_scale;
+  int pred_type;             /* 0 epsilon, 1 sample, 2 v_prediction */
+  float sqrt_alpha, sqrt_beta;
+  int clip;
+  float clip_range;
+  const void* sample;        /* x_t */
+  void* noise_pred;
+  void* pred_original_sample;
+} uav_cfg_step_t;
+uav_status_t uav_conv_out_cfg_step(const void* x, int64_t T, int64_t H, int64_t W, int64_t C, int64_t ld,
+                                   const float* affine, const void* w, const float* bias, int64_t Cout,
+                                   const uav_cfg_step_t* step, uav_stream_t stream);
+
 /* nn.LayerNorm over the last dim of fp16 tokens (attention.py:457,474,491,494). C % 8 == 0. */
 uav_status_t uav_layernorm(const void* x, int64_t rows, int64_t C, int64_t ld_in,
                            const float* gamma, const float* beta, float eps, void* y,

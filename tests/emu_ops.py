@@ -363,3 +363,18 @@ def wavelet_level(image, radius, *, low=None, high=None, high_first=False, add=N
 def pack_video_uint8(frames):
     v = (frames.float() / 2 + 0.5).clamp(0, 1) * 255
     return v.permute(0, 2, 3, 1).contiguous().to(torch.int32).to(torch.uint8)
+
+
+def conv_out_fused(x, gamma, beta, groups, eps, w, bias, cout, out_dtype, cfg_step=None):
+    """stand-in of ops.conv_out_fused: GroupNorm + SiLU (fp32, no rounding of the normalised tensor: the kernel applies it on
+    the way into shared memory, rounded to fp16 there), 3x3 conv, planar output; optional guidance + step_v0 epilogue"""
+    B, T, H, W, C = x.shape
+    y = group_norm(x, gamma, beta, groups, eps, silu=True, n_outer=B)
+    o = conv2d(y, w, bias, out_dtype=torch.float32)[..., :cout]
+    out = o.permute(0, 4, 1, 2, 3).contiguous()
+    if cfg_step is None:
+        return out.to(out_dtype)
+    npred = cfg_combine(out.half(), cfg_step["guidance_scale"])
+    x0 = ddim_step_v0(npred, cfg_step["sample"], cfg_step["pred_type"], cfg_step["sqrt_alpha"], cfg_step["sqrt_beta"],
+                      cfg_step["clip"], cfg_step["clip_range"])
+    return npred, x0

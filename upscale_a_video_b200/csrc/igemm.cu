@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (CL == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+              if (CL == 2) mbar_arrive_cluster_relaxed(tempty_leader + 8 * acc);
               else mbar_arrive(&tempty_bar[acc]);
             }
             // publish the staged tile to the async proxy and store it with TMA (clips OOB rows)
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-              if (CL == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+              if (CL == 2) mbar_arrive_cluster_relaxed(tempty_leader + 8 * acc);
               else mbar_arrive(&tempty_bar[acc]);
             }
         }

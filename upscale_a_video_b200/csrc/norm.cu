@@ -353,6 +353,28 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// affine[n][c] = {gamma[c] * rstd, beta[c] - mean * gamma[c] * rstd}: the per-(slab, channel) scale / shift of a GroupNorm,
+// for consumers that apply it themselves (uav_conv_out_fused)
+__global__ void gn_affine_kernel(const double* __restrict__ sums, int nsplit, int G, int C, double cnt,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 float2* __restrict__ affine) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int g = c / (C / G);
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < nsplit; ++k) {
+    s += sums[((static_cast<int64_t>(n) * G + g) * nsplit + k) * 2];
+    q += sums[((static_cast<int64_t>(n) * G + g) * nsplit + k) * 2 + 1];
+  }
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * rstd;
+  affine[static_cast<int64_t>(n) * C + c] = make_float2(sc, beta[c] - static_cast<float>(mean) * sc);
+}
+
 // ---------------------------------------------------------------------------------------
 // LayerNorm over the last dim (C % 8 == 0, C <= 2048): one warp per token
 // ---------------------------------------------------------------------------------------
@@ -538,6 +560,91 @@ uav_status_t uav_groupnorm_silu(const void* x, int64_t n_outer, int64_t pixels, 
   return UAV_OK;
 }
 
+// fp64 reduction of the producers' statistics blocks -> sums[n][g][S][2] at the head of `workspace`; returns S
+static uav_status_t gn_reduce_sources(int64_t n_outer, int64_t C, int groups, const uav_gn_source_t* sources, int n_sources,
+                                      void* workspace, size_t workspace_bytes, cudaStream_t stream, int* S_out) {
+  const int cpg = (int)(C / groups);
+  UAV_REQUIRE(cpg % 8 == 0, "groupnorm from partials: channels per group (%d) must be a multiple of 8", cpg);
+  UAV_REQUIRE(n_sources >= 1 && n_sources <= 4, "groupnorm from partials: 1..4 sources");
+  UAV_REQUIRE(workspace_bytes >= uav_groupnorm_workspace_bytes(n_outer, groups), "groupnorm from partials: workspace too small");
+  GnReduceParams prm;
+  memset(&prm, 0, sizeof(prm));
+  int oct = 0;
+  int64_t min_bps = INT64_MAX;
+  for (int i = 0; i < n_sources; ++i) {
+    const uav_gn_source_t& sc = sources[i];
+    UAV_REQUIRE(sc.partial && sc.C > 0 && sc.C % 8 == 0 && sc.blocks > 0 && (sc.slabs == n_outer || sc.slabs == 1) &&
+                    sc.blocks % sc.slabs == 0,
+                "groupnorm from partials: bad source %d (C=%lld blocks=%lld slabs=%lld)", i, (long long)sc.C,
+                (long long)sc.blocks, (long long)sc.slabs);
+    prm.src[i].p = reinterpret_cast<const float2*>(sc.partial);
+    prm.src[i].blocks = sc.blocks;
+    prm.src[i].bps = sc.blocks / sc.slabs;
+    prm.src[i].slab_mul = sc.slabs == n_outer ? 1 : 0;
+    prm.src[i].oct0 = oct;
+    prm.src[i].octs = (int)(sc.C / 8);
+    oct += (int)(sc.C / 8);
+    if (prm.src[i].bps < min_bps) min_bps = prm.src[i].bps;
+  }
+  UAV_REQUIRE(oct * 8 == C, "groupnorm from partials: sources cover %d channels, x has %lld", oct * 8, (long long)C);
+  prm.nsrc = n_sources;
+  prm.oct_per_group = cpg / 8;
+  prm.G = groups;
+  // enough CTAs to pull the blocks at HBM speed, at least ~256 blocks per split; GN_MAX_SPLIT doubles fit the workspace
+  int64_t S = (4 * (int64_t)num_sms() + groups * n_outer - 1) / (groups * n_outer);
+  if (S > min_bps / 256) S = min_bps / 256;
+  if (S > GN_MAX_SPLIT) S = GN_MAX_SPLIT;
+  if (S < 1) S = 1;
+  gn_reduce_partials_kernel<<<dim3((unsigned)groups, (unsigned)n_outer, (unsigned)S), 256, 0, stream>>>(
+      prm, reinterpret_cast<double*>(workspace));
+  UAV_CHECK_CUDA(cudaGetLastError());
+  *S_out = (int)S;
+  return UAV_OK;
+}
+
+uav_status_t uav_groupnorm_affine(const void* x, int64_t n_outer, int64_t pixels, int64_t C, int64_t ld_in, int groups,
+                                  const float* gamma, const float* beta, float eps, const uav_gn_source_t* sources,
+                                  int n_sources, float* affine, void* workspace, size_t workspace_bytes,
+                                  uav_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UAV_REQUIRE(gamma && beta && affine && workspace, "uav_groupnorm_affine: null pointer");
+  UAV_REQUIRE(n_outer > 0 && n_outer <= 65535 && pixels > 0 && C > 0 && C <= 2048 && groups > 0 && C % groups == 0,
+              "uav_groupnorm_affine: bad shape (C=%lld groups=%d)", (long long)C, groups);
+  double* sums = reinterpret_cast<double*>(workspace);
+  int S = 1;
+  int launches = 2;
+  if (n_sources > 0) {
+    UAV_REQUIRE(sources != nullptr, "uav_groupnorm_affine: null sources");
+    uav_status_t st = gn_reduce_sources(n_outer, C, groups, sources, n_sources, workspace, workspace_bytes, stream, &S);
+    if (st != UAV_OK) return st;
+  } else {
+    UAV_REQUIRE(x != nullptr && ld_in >= C && C % 8 == 0 && (C / groups) % 4 == 0 && ld_in % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                "uav_groupnorm_affine: without sources x must be an aligned fp16 tensor with C %% 8 == 0");
+    UAV_REQUIRE(workspace_bytes >= uav_groupnorm_workspace_bytes(n_outer, groups), "uav_groupnorm_affine: workspace too small");
+    float2* partial = reinterpret_cast<float2*>(sums + n_outer * groups * 2);
+    const int octs = (int)(C / 8);
+    const int pix_per_iter = GN_THREADS / octs;
+    int64_t want = ((int64_t)num_sms() * 8 + n_outer - 1) / n_outer;
+    int64_t maxb = ((pixels + pix_per_iter - 1) / pix_per_iter + 15) / 16;
+    int64_t gx = want < maxb ? want : maxb;
+    if (gx < 1) gx = 1;
+    if (gx > GN_MAX_BLOCKS_PER_N) gx = GN_MAX_BLOCKS_PER_N;
+    gn_stats_kernel<<<dim3((unsigned)gx, (unsigned)n_outer), GN_THREADS, 0, stream>>>(
+        reinterpret_cast<const __half*>(x), pixels, (int)C, ld_in, groups, partial);
+    UAV_CHECK_CUDA(cudaGetLastError());
+    gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)n_outer), 256, 0, stream>>>(partial, (int)gx, groups, sums);
+    UAV_CHECK_CUDA(cudaGetLastError());
+    launches = 3;
+  }
+  gn_affine_kernel<<<dim3((unsigned)((C + 255) / 256), (unsigned)n_outer), 256, 0, stream>>>(
+      sums, S, groups, (int)C, static_cast<double>(pixels) * (C / groups), gamma, beta, eps,
+      reinterpret_cast<float2*>(affine));
+  UAV_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  return UAV_OK;
+}
+
 uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, int64_t pixels, int64_t C,
                                               int64_t ld_in, int groups, const float* gamma, const float* beta,
                                               float eps, int silu, void* y, int64_t ld_out,
@@ -549,45 +656,15 @@ uav_status_t uav_groupnorm_silu_from_partials(const void* x, int64_t n_outer, in
   UAV_REQUIRE(n_outer > 0 && n_outer <= 65535 && pixels > 0 && C > 0 && C <= 2048 && groups > 0 && C % groups == 0 &&
                   ld_out >= C,
               "uav_groupnorm_silu_from_partials: bad shape (C=%lld groups=%d)", (long long)C, groups);
-  const int cpg = (int)(C / groups);
-  UAV_REQUIRE(cpg % 8 == 0, "uav_groupnorm_silu_from_partials: channels per group (%d) must be a multiple of 8", cpg);
   UAV_REQUIRE(C % 8 == 0 && (x == nullptr || (ld_in % 8 == 0 && ld_in >= C)) && ld_out % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
               "uav_groupnorm_silu_from_partials: tensors must be 16-byte aligned with ld %% 8 == 0");
-  UAV_REQUIRE(n_sources >= 1 && n_sources <= 4, "uav_groupnorm_silu_from_partials: 1..4 sources");
-  UAV_REQUIRE(workspace_bytes >= uav_groupnorm_workspace_bytes(n_outer, groups),
-              "uav_groupnorm_silu_from_partials: workspace too small");
-  GnReduceParams prm;
-  memset(&prm, 0, sizeof(prm));
-  int oct = 0;
-  int64_t min_bps = INT64_MAX;
-  for (int i = 0; i < n_sources; ++i) {
-    const uav_gn_source_t& sc = sources[i];
-    UAV_REQUIRE(sc.partial && sc.C > 0 && sc.C % 8 == 0 && sc.blocks > 0 && (sc.slabs == n_outer || sc.slabs == 1) &&
-                    sc.blocks % sc.slabs == 0,
-                "uav_groupnorm_silu_from_partials: bad source %d (C=%lld blocks=%lld slabs=%lld)", i, (long long)sc.C,
-                (long long)sc.blocks, (long long)sc.slabs);
-    prm.src[i].p = reinterpret_cast<const float2*>(sc.partial);
-    prm.src[i].blocks = sc.blocks;
-    prm.src[i].bps = sc.blocks / sc.slabs;
-    prm.src[i].slab_mul = sc.slabs == n_outer ? 1 : 0;
-    prm.src[i].oct0 = oct;
-    prm.src[i].octs = (int)(sc.C / 8);
-    oct += (int)(sc.C / 8);
-    if (prm.src[i].bps < min_bps) min_bps = prm.src[i].bps;
+  double* sums = reinterpret_cast<double*>(workspace);
+  int S = 1;
+  {
+    uav_status_t st = gn_reduce_sources(n_outer, C, groups, sources, n_sources, workspace, workspace_bytes, stream, &S);
+    if (st != UAV_OK) return st;
   }
-  UAV_REQUIRE(oct * 8 == C, "uav_groupnorm_silu_from_partials: sources cover %d channels, x has %lld", oct * 8, (long long)C);
-  prm.nsrc = n_sources;
-  prm.oct_per_group = cpg / 8;
-  prm.G = groups;
-  // enough CTAs to pull the blocks at HBM speed, at least ~256 blocks per split; GN_MAX_SPLIT doubles fit the workspace
-  int64_t S = (4 * (int64_t)num_sms() + groups * n_outer - 1) / (groups * n_outer);
-  if (S > min_bps / 256) S = min_bps / 256;
-  if (S > GN_MAX_SPLIT) S = GN_MAX_SPLIT;
-  if (S < 1) S = 1;
-  double* sums = reinterpret_cast<double*>(workspace);  // [n][g][S][2] <= the stats-kernel partial area
-  gn_reduce_partials_kernel<<<dim3((unsigned)groups, (unsigned)n_outer, (unsigned)S), 256, 0, stream>>>(prm, sums);
-  UAV_CHECK_CUDA(cudaGetLastError());
   // apply: one launch over x, or — when the sources carry their own tensors (a concat that was never materialised) — one
   // launch per source, each writing its channel range of the dense output
   const bool per_source = sources[0].x != nullptr;

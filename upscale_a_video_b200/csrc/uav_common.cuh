@@ -118,6 +118,13 @@ __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, ui
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// arrive WITHOUT a memory fence.  The release form above compiles to MEMBAR.ALL.CTA + ERRBAR (14 % of the epilogue warps'
+// stall samples in the GEGLU GEMM, ncu round 2).  Used to hand a tensor-memory accumulator back to the MMA warp: the only
+// accesses that must be ordered before the arrive are the tcgen05.ld reads, which tcgen05.fence::before_thread_sync
+// (issued before the arrive) / ::after_thread_sync (after the wait) order on their own.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // wait with cluster-scope acquire (the arrivals come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(

@@ -86,13 +86,19 @@ def _pixel_ld(x: torch.Tensor) -> int:
     assert x.stride(-1) == 1 or x.shape[-1] == 1, "channel dim must be contiguous"
     if x.dim() == 1:
         return x.shape[0]
-    ld = x.stride(-2)
-    exp = ld
+    # the pixel stride is the stride of the innermost pixel dim of extent > 1 (a size-1 dim reports an arbitrary stride:
+    # e.g. the (b, t, h*w = 1, c) view of a channel slice of a wider buffer)
+    ld = None
+    exp = None
     for d in range(x.dim() - 2, -1, -1):
         if x.shape[d] != 1:
+            if ld is None:
+                ld = x.stride(d)
+                exp = ld
             assert x.stride(d) == exp, f"tensor is not a dense channels-last view: {x.shape} {x.stride()}"
-        exp *= x.shape[d]
-    return ld
+        if exp is not None:
+            exp *= x.shape[d]
+    return x.shape[-1] if ld is None else ld
 
 
 class GnStats:
@@ -323,14 +329,7 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     lib = _lib.load()
     nbytes = lib.uav_groupnorm_workspace_bytes(n_outer, groups)
     ws = _gn_workspace(x.device, nbytes)
-    srcs = None
-    if stats and (C // groups) % 8 == 0 and len(stats) <= 4 and sum(s.C for s in stats) == C:
-        b = x.shape[0] if batch is None else batch
-        slabs = [s.slabs_for(n_outer, b) for s in stats]
-        if all(slabs):
-            srcs = (_lib.GnSource * len(stats))()
-            for i, (s, sl) in enumerate(zip(stats, slabs)):
-                srcs[i].partial, srcs[i].blocks, srcs[i].C, srcs[i].slabs = s.partial.data_ptr(), s.blocks, s.C, sl
+    srcs = _gn_sources(x, stats, groups, n_outer, x.shape[0] if batch is None else batch)
     if srcs is not None:
         with _timed("groupnorm", 0.0, 2.0 * 2 * total_pix * C, f"gn(fused stats) {total_pix}px C{C}"):  # read + write
             _lib.check(lib.uav_groupnorm_silu_from_partials(x.data_ptr(), n_outer, pixels, C, _pixel_ld(x), groups,
@@ -383,6 +382,60 @@ def group_norm_cat(parts, gamma: torch.Tensor, beta: torch.Tensor, groups: int, 
                                                         eps, 1 if silu else 0, out.data_ptr(), C, srcs, len(parts),
                                                         ws.data_ptr(), ws.numel(), _stream()),
                    "uav_groupnorm_silu_from_partials")
+    return out
+
+
+def _gn_sources(x, stats, groups: int, n_outer: int, batch: int):
+    """ctypes source table for a tensor whose producer(s) emitted GroupNorm statistics, or None"""
+    C = x.shape[-1]
+    if not (GN_FUSED_STATS and stats and (C // groups) % 8 == 0 and len(stats) <= 4 and sum(s.C for s in stats) == C):
+        return None
+    slabs = [s.slabs_for(n_outer, batch) for s in stats]
+    if not all(slabs):
+        return None
+    srcs = (_lib.GnSource * len(stats))()
+    for i, (s, sl) in enumerate(zip(stats, slabs)):
+        srcs[i].partial, srcs[i].blocks, srcs[i].C, srcs[i].slabs = s.partial.data_ptr(), s.blocks, s.C, sl
+    return srcs
+
+
+def conv_out_fused(x: torch.Tensor, gamma, beta, groups: int, eps: float, w: torch.Tensor, bias, cout: int, out_dtype,
+                   cfg_step: Optional[dict] = None):
+    """conv_out(SiLU(GroupNorm(x))) -> planar (B, cout, T, H, W): x (B, T, H, W, 256) fp16 raw, w (cout, 3, 3, 256) fp16
+    (unet_video.py:567-569).  GroupNorm statistics from x's producer when it emitted them, else by a read pass.
+    `cfg_step` (B == 2, fp16): dict(guidance_scale, pred_type, sqrt_alpha, sqrt_beta, clip, clip_range, sample) — the
+    classifier-free-guidance combine and DDIMScheduler.step_v0 run in the kernel's epilogue; returns (noise_pred, x0), both
+    (1, cout, T, H, W) fp16, bit-identical to cfg_combine + ddim_step_v0 on the unfused output."""
+    B, T, H, W, C = x.shape
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous() and tuple(w.shape[1:]) == (3, 3, C)
+    lib = _lib.load()
+    ws = _gn_workspace(x.device, lib.uav_groupnorm_workspace_bytes(B, groups))
+    affine = torch.empty(B, C, 2, dtype=torch.float32, device=x.device)
+    stats = getattr(x, "uav_gn", None)
+    srcs = _gn_sources(x, stats, groups, B, B)
+    with _timed("groupnorm", 0.0, 2.0 * x.numel() if srcs is None else 0.0, f"gn affine {x.numel() // C}px C{C}"):
+        _lib.check(lib.uav_groupnorm_affine(x.data_ptr(), B, T * H * W, C, _pixel_ld(x), groups, gamma.data_ptr(),
+                                            beta.data_ptr(), eps, srcs, 0 if srcs is None else len(stats),
+                                            affine.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "uav_groupnorm_affine")
+    bias_p = None if bias is None else bias.data_ptr()
+    if cfg_step is not None:
+        sample = cfg_step["sample"]
+        assert B == 2 and sample.dtype == torch.float16 and sample.is_contiguous() and tuple(sample.shape) == (1, cout, T, H, W)
+        noise_pred, x0 = torch.empty_like(sample), torch.empty_like(sample)
+        st = _lib.CfgStep(float(cfg_step["guidance_scale"]), int(cfg_step["pred_type"]), float(cfg_step["sqrt_alpha"]),
+                          float(cfg_step["sqrt_beta"]), 1 if cfg_step["clip"] else 0, float(cfg_step["clip_range"]),
+                          sample.data_ptr(), noise_pred.data_ptr(), x0.data_ptr())
+        with _timed("conv_io", 2.0 * B * T * H * W * cout * C * 9, 2.0 * x.numel() + 6.0 * sample.numel(),
+                    f"conv_out+cfg+step_v0 {B * T}x{H}x{W} {C}->{cout}"):
+            _lib.check(lib.uav_conv_out_cfg_step(x.data_ptr(), T, H, W, C, _pixel_ld(x), affine.data_ptr(), w.data_ptr(),
+                                                 bias_p, cout, C.byref(st), _stream()), "uav_conv_out_cfg_step")
+        return noise_pred, x0
+    out = torch.empty(B, cout, T, H, W, dtype=out_dtype, device=x.device)
+    with _timed("conv_io", 2.0 * B * T * H * W * cout * C * 9, 2.0 * x.numel() + out.numel() * out.element_size(),
+                f"conv_out_fused {B * T}x{H}x{W} {C}->{cout}"):
+        _lib.check(lib.uav_conv_out_fused(x.data_ptr(), B, T, H, W, C, _pixel_ld(x), affine.data_ptr(), w.data_ptr(),
+                                          bias_p, cout, out.data_ptr(), F16 if out_dtype == torch.float16 else F32,
+                                          _stream()), "uav_conv_out_fused")
     return out
 
 

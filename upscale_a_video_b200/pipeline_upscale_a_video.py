@@ -20,6 +20,7 @@ from typing import Any, List, Optional, Union
 import torch
 
 from . import _lib, ops, sharding
+from .scheduling_ddim import _PRED
 from ._config import ConfigMixin
 from ._lib import UavError
 
@@ -274,7 +275,11 @@ class VideoUpscalePipeline(ConfigMixin):
         units = sharding.window_units(len(uniq), world, can_split=do_cfg and image.shape[0] == 2)
         split = bool(units) and units[0][1] >= 0
         pe_half = [prompt_embeds[0:1], prompt_embeds[1:2]] if split else None
+        fuse_step = (do_cfg and dtype == torch.float16 and batch_size * num_images_per_prompt == 1 and
+                     "cfg_step" in inspect.signature(self.unet.forward).parameters and hasattr(self.scheduler, "_coefs")
+                     and getattr(self.scheduler.config, "prediction_type", None) in _PRED)
         for i, t in enumerate(timesteps):
+            x0_fused = None
             lat_in = torch.cat([latents] * 2) if do_cfg else latents
             if T > sharding.SHORT_SEQ:
                 local = {}
@@ -302,11 +307,26 @@ class VideoUpscalePipeline(ConfigMixin):
                         covered[s + k] = True
                     ops.window_blend(noise_pred, outs[uniq.index((s, e))].contiguous(), s, mask)
             else:
-                noise_pred = self.unet(lat_in, t, image, encoder_hidden_states=prompt_embeds, class_labels=noise_level_t,
-                                       **shared).sample
-            if do_cfg:
-                noise_pred = ops.cfg_combine(noise_pred.contiguous(), float(guidance_scale))
-            x0 = self.scheduler.step_v0(noise_pred, t, latents, **extra).pred_original_sample
+                # single window: guidance combine + step_v0 ride the UNet's last kernel (conv_out epilogue) when both the
+                # UNet and the scheduler are ours; bit-identical to the three separate kernels below
+                fused = None
+                if fuse_step:
+                    cf = self.scheduler._coefs(t)
+                    fused = dict(guidance_scale=float(guidance_scale), pred_type=_PRED[self.scheduler.config.prediction_type],
+                                 sqrt_alpha=cf["sa"], sqrt_beta=cf["sb"], clip=bool(self.scheduler.config.clip_sample),
+                                 clip_range=float(self.scheduler.config.clip_sample_range), sample=latents.contiguous())
+                r = self.unet(lat_in, t, image, encoder_hidden_states=prompt_embeds, class_labels=noise_level_t,
+                              **shared, **({"cfg_step": fused} if fused is not None else {}))
+                if hasattr(r, "pred_original_sample"):
+                    noise_pred, x0_fused = r.noise_pred, r.pred_original_sample
+                else:
+                    noise_pred = r.sample
+            if x0_fused is not None:
+                x0 = x0_fused
+            else:
+                if do_cfg:
+                    noise_pred = ops.cfg_combine(noise_pred.contiguous(), float(guidance_scale))
+                x0 = self.scheduler.step_v0(noise_pred, t, latents, **extra).pred_original_sample
             if use_prop and i in propagation_steps:
                 x0 = self.propagator(x0, ff, fb, interpolation="nearest", mode="fuse", fuse_scale=0.5, alpha1=0.001, alpha2=0.05)
             latents = self.scheduler.step_vt(x0, noise_pred, t, latents, **extra).prev_sample

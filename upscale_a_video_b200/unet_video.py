@@ -40,6 +40,13 @@ class UNet3DConditionOutput:
         return (self.sample,)[i]
 
 
+@dataclass
+class UNetCfgStepOutput:
+    """forward(..., cfg_step=...): the guidance combine and DDIMScheduler.step_v0 ran in conv_out's epilogue"""
+    noise_pred: torch.Tensor            # (1, c, t, h, w): u + g (c - u)
+    pred_original_sample: torch.Tensor  # (1, c, t, h, w): step_v0(noise_pred, t, sample)
+
+
 class TimestepEmbedding(nn.Module):
     """diffusers TimestepEmbedding parameter holder (unet_video.py:176)"""
 
@@ -51,6 +58,9 @@ class TimestepEmbedding(nn.Module):
 
 # compute the text-independent UNet prefix once for both classifier-free-guidance halves (UAV_SHARE_CFG_PREFIX=0: off)
 SHARE_CFG_PREFIX = os.environ.get("UAV_SHARE_CFG_PREFIX", "1") != "0"
+
+# conv_norm_out + SiLU + conv_out + layout conversion as one kernel (csrc/conv_io.cu); UAV_FUSED_CONV_OUT=0: separate kernels
+FUSED_CONV_OUT = os.environ.get("UAV_FUSED_CONV_OUT", "1") != "0"
 
 _DOWN = {"DownBlock3D": DownBlock3D, "CrossAttnDownBlock3D": CrossAttnDownBlock3D}
 _UP = {"UpBlock3D": UpBlock3D, "CrossAttnUpBlock3D": CrossAttnUpBlock3D}
@@ -212,11 +222,15 @@ class UNetVideoModel(PackedModule, ConfigMixin):
     # ------------------------------------------------------------------ forward (unet_video.py:404-574)
     @torch.no_grad()
     def forward(self, sample, timestep, low_res, encoder_hidden_states=None, class_labels=20, attention_mask=None,
-                return_dict: bool = True, *, cfg_shared_input: bool = False):
+                return_dict: bool = True, *, cfg_shared_input: bool = False, cfg_step: Optional[dict] = None):
         """`cfg_shared_input` (keyword-only extension, set by VideoUpscalePipeline): the two batch items are the
         classifier-free-guidance halves of the SAME latents / LR frames / noise level (pipeline...:614,551), so everything
         before the first text-conditioned layer (conv_in, down block 0, its temporal module, the first resnet of down
-        block 1) is identical for both and is computed once (SURVEY.md §7.2 iii: exact work removal, ~3.6 % of the FLOPs)."""
+        block 1) is identical for both and is computed once (SURVEY.md §7.2 iii: exact work removal, ~3.6 % of the FLOPs).
+        `cfg_step` (keyword-only extension, set by VideoUpscalePipeline for the single-window case): dict(guidance_scale,
+        pred_type, sqrt_alpha, sqrt_beta, clip, clip_range, sample) — classifier-free guidance and DDIMScheduler.step_v0
+        (pipeline...:644-649) run in conv_out's epilogue and a UNetCfgStepOutput is returned; ignored (plain output) when
+        the fused tail does not apply (batch != 2, fp32 working dtype, UAV_FUSED_CONV_OUT=0)."""
         _lib.require_cuda(sample, "UNetVideoModel.forward")
         if attention_mask is not None:
             raise NotImplementedError("attention_mask is never passed by VideoUpscalePipeline")
@@ -313,10 +327,21 @@ class UNetVideoModel(PackedModule, ConfigMixin):
             _tap(f"up{i}", x)
             x = tmod(c, x, out=None if t_empty else slot)
             _tap(f"up_temp{i}", x)
-        x = _gn(c, self.conv_norm_out, x, True, B)
-        x = self.conv_out.run(c, x)
-        out = ops.channels_last_to_planar(x, cfg.out_channels, sample.dtype if sample.dtype in
-                                          (torch.float16, torch.float32) else torch.float16)
+        out_dtype = sample.dtype if sample.dtype in (torch.float16, torch.float32) else torch.float16
+        if FUSED_CONV_OUT and x.shape[-1] == 256 and cfg.out_channels <= 5 and x.shape[0] == B:
+            # GroupNorm apply + SiLU + conv_out + the rearrange to "b c t h w" in ONE pass over the 256-channel tensor
+            g, bt = c.pk.affine(self.conv_norm_out)
+            w, bias = c.pk.conv(self.conv_out)
+            if cfg_step is not None and B == 2 and out_dtype == torch.float16 and cfg_step["sample"].dtype == torch.float16:
+                npred, x0 = ops.conv_out_fused(x, g, bt, self.conv_norm_out.num_groups, self.conv_norm_out.eps, w, bias,
+                                               cfg.out_channels, out_dtype, cfg_step=cfg_step)
+                return UNetCfgStepOutput(noise_pred=npred, pred_original_sample=x0)
+            out = ops.conv_out_fused(x, g, bt, self.conv_norm_out.num_groups, self.conv_norm_out.eps, w, bias,
+                                     cfg.out_channels, out_dtype)
+        else:
+            x = _gn(c, self.conv_norm_out, x, True, B)
+            x = self.conv_out.run(c, x)
+            out = ops.channels_last_to_planar(x, cfg.out_channels, out_dtype)
         if not return_dict:
             return (out,)
         return UNet3DConditionOutput(sample=out)
