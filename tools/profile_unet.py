@@ -41,13 +41,20 @@ def run(tag, detail=False):
 
 run("default", detail=True)
 if "--ab" in sys.argv:
-    ops.GN_FUSED_STATS = False
-    run("GN statistics by their own pass (UAV_GN_FUSED_STATS=0)")
-    ops.GN_FUSED_STATS = True
+    from upscale_a_video_b200 import unet_video
     layers.GN_STATS_LINEAR = False
     run("no statistics from Linear / 1x1 producers (UAV_GN_STATS_LINEAR=0)")
     layers.GN_STATS_LINEAR = True
-    layers.INPLACE_CONCAT = False
-    run("skip concat by two copies (UAV_INPLACE_CONCAT=0)")
-    layers.INPLACE_CONCAT = True
+    layers.VIRTUAL_CONCAT = False
+    run("concat buffers, main branch in place (UAV_VIRTUAL_CONCAT=0)")
+    layers.GN_STATS_LINEAR = False
+    run("UAV_VIRTUAL_CONCAT=0 + UAV_GN_STATS_LINEAR=0")
+    layers.GN_STATS_LINEAR = True
+    layers.VIRTUAL_CONCAT = True
+    unet_video.FUSED_CONV_OUT = False
+    run("separate conv_norm_out / conv_out kernels (UAV_FUSED_CONV_OUT=0)")
+    unet_video.FUSED_CONV_OUT = True
+    ops.GN_FUSED_STATS = False
+    run("GN statistics by their own pass (UAV_GN_FUSED_STATS=0)")
+    ops.GN_FUSED_STATS = True
     run("default again")
