@@ -331,7 +331,7 @@ def test_groupnorm_of_a_concat_that_is_never_built():
     """ops.group_norm_cat: GroupNorm(cat([x, skip])) -> dense tensor, the two inputs read in place (one apply launch per
     part), statistics from their producers; a batch-1 skip serves both batch items; groups straddle the boundary"""
     torch.manual_seed(5)
-    B, T, H, W = 2, 3, 12, 20
+    B, T, H, W = 2, 3, 16, 24   # t*h*w = 9 x 128 rows per batch item: a Linear producer's blocks split per batch item
     for cx, cs, skip_b in ((1024, 512, 1), (512, 256, 2), (256, 256, 1)):
         x = ops.conv2d(_rand(B, T, H, W, 64), _rand(cx, 3, 3, 64, scale=0.05), None, gn_stats=True)
         skip = ops.linear(_rand(skip_b, T, H * W, 128), _rand(cs, 128, scale=0.1), torch.randn(cs, device=DEV), gn_stats=True)

@@ -406,15 +406,15 @@ def conv_out_fused(x: torch.Tensor, gamma, beta, groups: int, eps: float, w: tor
     `cfg_step` (B == 2, fp16): dict(guidance_scale, pred_type, sqrt_alpha, sqrt_beta, clip, clip_range, sample) — the
     classifier-free-guidance combine and DDIMScheduler.step_v0 run in the kernel's epilogue; returns (noise_pred, x0), both
     (1, cout, T, H, W) fp16, bit-identical to cfg_combine + ddim_step_v0 on the unfused output."""
-    B, T, H, W, C = x.shape
-    assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous() and tuple(w.shape[1:]) == (3, 3, C)
+    B, T, H, W, Cc = x.shape
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous() and tuple(w.shape[1:]) == (3, 3, Cc)
     lib = _lib.load()
     ws = _gn_workspace(x.device, lib.uav_groupnorm_workspace_bytes(B, groups))
-    affine = torch.empty(B, C, 2, dtype=torch.float32, device=x.device)
+    affine = torch.empty(B, Cc, 2, dtype=torch.float32, device=x.device)
     stats = getattr(x, "uav_gn", None)
     srcs = _gn_sources(x, stats, groups, B, B)
-    with _timed("groupnorm", 0.0, 2.0 * x.numel() if srcs is None else 0.0, f"gn affine {x.numel() // C}px C{C}"):
-        _lib.check(lib.uav_groupnorm_affine(x.data_ptr(), B, T * H * W, C, _pixel_ld(x), groups, gamma.data_ptr(),
+    with _timed("groupnorm", 0.0, 2.0 * x.numel() if srcs is None else 0.0, f"gn affine {x.numel() // Cc}px C{Cc}"):
+        _lib.check(lib.uav_groupnorm_affine(x.data_ptr(), B, T * H * W, Cc, _pixel_ld(x), groups, gamma.data_ptr(),
                                             beta.data_ptr(), eps, srcs, 0 if srcs is None else len(stats),
                                             affine.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "uav_groupnorm_affine")
     bias_p = None if bias is None else bias.data_ptr()
@@ -425,15 +425,15 @@ def conv_out_fused(x: torch.Tensor, gamma, beta, groups: int, eps: float, w: tor
         st = _lib.CfgStep(float(cfg_step["guidance_scale"]), int(cfg_step["pred_type"]), float(cfg_step["sqrt_alpha"]),
                           float(cfg_step["sqrt_beta"]), 1 if cfg_step["clip"] else 0, float(cfg_step["clip_range"]),
                           sample.data_ptr(), noise_pred.data_ptr(), x0.data_ptr())
-        with _timed("conv_io", 2.0 * B * T * H * W * cout * C * 9, 2.0 * x.numel() + 6.0 * sample.numel(),
-                    f"conv_out+cfg+step_v0 {B * T}x{H}x{W} {C}->{cout}"):
-            _lib.check(lib.uav_conv_out_cfg_step(x.data_ptr(), T, H, W, C, _pixel_ld(x), affine.data_ptr(), w.data_ptr(),
+        with _timed("conv_io", 2.0 * B * T * H * W * cout * Cc * 9, 2.0 * x.numel() + 6.0 * sample.numel(),
+                    f"conv_out+cfg+step_v0 {B * T}x{H}x{W} {Cc}->{cout}"):
+            _lib.check(lib.uav_conv_out_cfg_step(x.data_ptr(), T, H, W, Cc, _pixel_ld(x), affine.data_ptr(), w.data_ptr(),
                                                  bias_p, cout, C.byref(st), _stream()), "uav_conv_out_cfg_step")
         return noise_pred, x0
     out = torch.empty(B, cout, T, H, W, dtype=out_dtype, device=x.device)
-    with _timed("conv_io", 2.0 * B * T * H * W * cout * C * 9, 2.0 * x.numel() + out.numel() * out.element_size(),
-                f"conv_out_fused {B * T}x{H}x{W} {C}->{cout}"):
-        _lib.check(lib.uav_conv_out_fused(x.data_ptr(), B, T, H, W, C, _pixel_ld(x), affine.data_ptr(), w.data_ptr(),
+    with _timed("conv_io", 2.0 * B * T * H * W * cout * Cc * 9, 2.0 * x.numel() + out.numel() * out.element_size(),
+                f"conv_out_fused {B * T}x{H}x{W} {Cc}->{cout}"):
+        _lib.check(lib.uav_conv_out_fused(x.data_ptr(), B, T, H, W, Cc, _pixel_ld(x), affine.data_ptr(), w.data_ptr(),
                                           bias_p, cout, out.data_ptr(), F16 if out_dtype == torch.float16 else F32,
                                           _stream()), "uav_conv_out_fused")
     return out
