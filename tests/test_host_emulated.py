@@ -103,6 +103,23 @@ def test_vae_host_logic_vs_golden(emulated):
     assert e < 1e-2
 
 
+def test_vae_encode_odd_size_host_logic(emulated):
+    """Downsample3D(padding=0) on an odd size = F.pad (0,1,0,1) + unpadded stride-2 conv -> floor((H-2)/2)+1 rows
+    (resnet.py:188-192): 90 -> 45 -> 22, not 23"""
+    from oracle import uav_oracle as O
+    from oracle.weights import make_state_dict
+    meta = json.load(open(os.path.join(G, "meta.json")))
+    cfg = json.load(open(os.path.join(CFG, "vae_3d_config.json")))
+    sd = make_state_dict(json.load(open(os.path.join(G, "shapes_vae_3d.json"))), meta["seed_vae"])
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(1, 3, 2, 90, 74, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref = O.vae_encode_moments(sd, cfg, x)
+    mom = _vae("vae_3d").encode(x).latent_dist.parameters
+    assert mom.shape == ref.shape == (1, 8, 2, 22, 18)
+    assert _rel(mom, ref) < 1e-2
+
+
 def _hot_vae_state_dict(kind):
     """vae state dict whose up-block branch outputs are ~3e4 x larger: the decoder's residual stream leaves the fp16 range
     (what the shipped x4-upscaler VAE does: "overflows in float16", pipeline_upscale_a_video.py:667-669)"""

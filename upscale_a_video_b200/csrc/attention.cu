@@ -409,10 +409,11 @@ __global__ void __launch_bounds__(FA_THREADS)
 template <int D, int NB16>
 static uav_status_t launch_cross(const FaParams& p, int batch, cudaStream_t stream) {
   constexpr int smem = (2 * NB16 * 16 * D + 2 * FA_BM * D) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per-device bit: cudaFuncSetAttribute applies to the current device only
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
+  if (!(configured & dev_bit)) {
     UAV_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_kernel<D, NB16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured |= dev_bit;
   }
   const int ntiles = (p.nq + FA_BM - 1) / FA_BM;
   // enough CTAs to fill the GPU ~4x over, each streaming several query tiles past its resident K/V
@@ -725,11 +726,12 @@ uav_status_t attention_tc(const void* q, const void* k, const void* v, void* out
 template <int DQK, int DV>
 static uav_status_t launch_fa(const FaParams& p, int batch, cudaStream_t stream) {
   constexpr int smem = (FA_BM * DQK + 2 * FA_BN * DQK + 2 * FA_BN * DV) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per-device bit: cudaFuncSetAttribute applies to the current device only
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
+  if (!(configured & dev_bit)) {
     UAV_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<DQK, DV>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured |= dev_bit;
   }
   dim3 grid((p.nq + FA_BM - 1) / FA_BM, batch * p.heads);
   flash_attn_kernel<DQK, DV><<<grid, FA_THREADS, smem, stream>>>(p);

@@ -383,12 +383,13 @@ static uav_status_t make_map_3d(CUtensorMap* map, const void* base, int64_t cols
 template <int DQK, int DVT>
 static uav_status_t launch_fa_tc(FaTcParams& p, int64_t batch, int dv_splits, cudaStream_t stream) {
   using Cfg = FaTcCfg<DQK, DVT>;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per-device bit: cudaFuncSetAttribute applies to the current device only
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
+  if (!(configured & dev_bit)) {
     UAV_CHECK_CUDA(cudaFuncSetAttribute(fa_tc_kernel<DQK, DVT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    configured = true;
+    configured |= dev_bit;
   }
   dim3 grid((p.nq + TC_BM - 1) / TC_BM, dv_splits, (unsigned)(batch * p.heads));
   fa_tc_kernel<DQK, DVT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(p);

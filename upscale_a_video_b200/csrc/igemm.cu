@@ -45,15 +45,21 @@ void set_last_error(const char* fmt, ...) {
 }
 std::atomic<uint64_t> g_launches{0};
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};  // per device (a process may drive several GPUs)
+  const int dev = current_device() & 63;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 PFN_encodeTiled get_encode_tiled() {
@@ -777,11 +783,12 @@ struct IgemmDesc {
 template <int BLOCK_N, bool GEGLU, bool TMA_EPI, bool AUX, int CL>
 static uav_status_t launch_instance3(IgemmParams& p, cudaStream_t stream) {
   using Cfg = IgemmCfg<BLOCK_N, GEGLU>;
-  static bool configured = false;
+  static uint64_t configured = 0;  // per-device bit: cudaFuncSetAttribute applies to the current device only
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
   auto kern = igemm_kernel<BLOCK_N, GEGLU, TMA_EPI, AUX, CL>;
-  if (!configured) {
+  if (!(configured & dev_bit)) {
     UAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    configured |= dev_bit;
   }
   const uint32_t sms = (uint32_t)num_sms();
   cudaLaunchConfig_t cfg;

@@ -33,7 +33,8 @@ void set_last_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
-int num_sms();
+int num_sms();         // of the current device
+int current_device();
 
 // ---------------------------------------------------------------------------------------
 // device helpers

@@ -161,7 +161,14 @@ class InflatedConv3d(nn.Conv2d):
                 xp = torch.zeros(*x.shape[:-3], H + H % 2, W + W % 2, x.shape[-1], dtype=x.dtype, device=x.device)
                 xp[..., :H, :W, :].copy_(x)  # strided plumbing copy (only for odd sizes, e.g. 45 -> 23 at 180x320)
                 x = xp
-            return self._launch(x, w, b, dict(stride=2, pad_mode=pad_mode), epi)
+            y = self._launch(x, w, b, dict(stride=2, pad_mode=pad_mode), epi)
+            if pad_mode == 1 and (H % 2 or W % 2):
+                # F.pad (0,1,0,1) + unpadded stride-2 conv (resnet.py:188-192) yields floor((H - 2) / 2) + 1 rows: for an odd
+                # H the even-padded launch computed one extra row / column from padding only — drop it
+                ho, wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+                if (ho, wo) != tuple(y.shape[-3:-1]):
+                    y = y[..., :ho, :wo, :].contiguous()
+            return y
         return self._launch(x, w, b, {}, epi)
 
     @staticmethod

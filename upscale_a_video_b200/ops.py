@@ -83,6 +83,9 @@ class _timed:
 def _pixel_ld(x: torch.Tensor) -> int:
     """element distance between consecutive pixels; validates the channels-last layout"""
     assert x.is_cuda, "uav_b200 ops need CUDA tensors (no CPU fallback)"
+    # kernels launch on the CURRENT device's stream: a tensor living elsewhere would be dereferenced on the wrong GPU
+    assert x.device.index == torch.cuda.current_device(), \
+        f"tensor on cuda:{x.device.index} but the current device is cuda:{torch.cuda.current_device()} (torch.cuda.set_device first)"
     assert x.stride(-1) == 1 or x.shape[-1] == 1, "channel dim must be contiguous"
     if x.dim() == 1:
         return x.shape[0]

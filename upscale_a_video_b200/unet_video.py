@@ -354,9 +354,13 @@ class UNetVideoModel(PackedModule, ConfigMixin):
             if int(torch.as_tensor(orig).max()) > mx:
                 raise ValueError(f"`noise_level` has to be <= {mx} but is {orig}")
             return
-        key = (orig.data_ptr(), orig._version)
-        seen = self.__dict__.setdefault("_nl_checked", set())
-        if key not in seen:
-            if bool(torch.any(cl > mx)):
-                raise ValueError(f"`noise_level` has to be <= {mx} but is {orig}")
-            seen.add(key)
+        # memo keyed on the tensor OBJECT (held alive by the entry, so its storage cannot be recycled for other labels while the
+        # entry exists — a data_ptr key would go stale) and its version counter; a handful of entries at most
+        seen = self.__dict__.setdefault("_nl_checked", [])
+        for ref, ver in seen:
+            if ref is orig and ver == orig._version:
+                return
+        if bool(torch.any(cl > mx)):
+            raise ValueError(f"`noise_level` has to be <= {mx} but is {orig}")
+        seen.append((orig, orig._version))
+        del seen[:-4]
