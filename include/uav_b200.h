@@ -85,7 +85,22 @@ typedef struct {
    * epilogue (n_out >= 33, aligned) and no GEGLU.  Deterministic (no atomics). */
   void* gn_partial;
   int64_t gn_blocks;
+  /* nn.LayerNorm folded into the Linear that consumes it (attention.py:525-563: norm1/2/temporal/3 -> to_q / q|k|v / GEGLU):
+   * the GEMM runs on the RAW rows x (K = normalised width) against W' = W * gamma (caller-packed), and the epilogue applies
+   *   LN(x) W^T + b  =  rstd[row] * (acc - mean[row] * colsum(W')[n]) + b'[n],     b' = b + W beta (passed as `bias`)
+   * so the normalised tensor is never written or read.  mean / rstd come from ln_in: fp32 [M][ln_slots][2] = partial
+   * {sum, sum of squares} of each input row, written by the Linear that PRODUCED x through ln_out (one slot per
+   * 128-column half of its N-tiles: ln_out_slots must equal uav_ln_partial_slots(N) of that launch).  Linear only. */
+  const void* ln_in;
+  const float* ln_colsum; /* fp32 [N]: sum over k of the fp16 W'[n][k] */
+  int ln_slots;
+  float ln_eps;
+  void* ln_out;
+  int ln_out_slots;
 } uav_epilogue_t;
+
+/* slots per row a Linear with n_out output columns writes through ln_out */
+int uav_ln_partial_slots(int64_t n_out);
 
 /* number of 32-row statistics blocks the implicit-GEMM launch over `images` images of `w` x `h` output pixels
  * produces (4 per M-tile; an M-tile is a tw x th = 128 pixel rectangle of one image, or 128 rows when h == 1) */

@@ -38,6 +38,12 @@ class Epilogue(C.Structure):
         ("out_scale", C.c_float),
         ("gn_partial", C.c_void_p),
         ("gn_blocks", C.c_int64),
+        ("ln_in", C.c_void_p),
+        ("ln_colsum", C.c_void_p),
+        ("ln_slots", C.c_int),
+        ("ln_eps", C.c_float),
+        ("ln_out", C.c_void_p),
+        ("ln_out_slots", C.c_int),
     ]
 
 
@@ -110,6 +116,7 @@ _SPECIAL = {
     "uav_launch_count": (C.c_uint64, []),
     "uav_groupnorm_workspace_bytes": (C.c_size_t, [I64, I32]),
     "uav_gn_partial_blocks": (C.c_int64, [I64, I64, I64]),
+    "uav_ln_partial_slots": (C.c_int, [I64]),
     "uav_plane_stats_workspace_bytes": (C.c_size_t, [I64]),
     "uav_instnorm_workspace_bytes": (C.c_size_t, [I64, I64]),
 }

@@ -122,6 +122,14 @@ struct alignas(64) IgemmParams {
   float out_scale;     // applied before the residual add (1 = off)
   float* gn_partial;   // [n_out / 8][gn_blocks][2] GroupNorm statistics of the output, or nullptr
   int64_t gn_blocks;
+  // LayerNorm folded into the GEMM (see uav_epilogue_t): per-row {sum, sumsq} slots of the INPUT rows written by its
+  // producer, the column sums of the gamma-scaled weight, and (as a producer) the slots of the OUTPUT rows
+  const float2* ln_in;
+  const float* ln_colsum;
+  int32_t ln_slots;
+  float ln_inv_c, ln_eps;
+  float2* ln_out;
+  int32_t ln_out_slots;
 };
 
 template <int BLOCK_N, bool GEGLU>
@@ -501,6 +509,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 res_phase ^= 1;
               }
             }
+            // LayerNorm of the input rows folded into this GEMM: acc was computed on the RAW rows x against W' = W * gamma, so
+            // LN(x) W^T + b = rstd * (acc - mean * colsum(W')) + b'  with the row statistics emitted by x's producer
+            float ln_a = 1.0f, ln_b = 0.0f;
+            float ln_s = 0.f, ln_q = 0.f;  // statistics of THIS tile's output row (for the next LayerNorm)
+            if constexpr (AUX) {
+              if (p.ln_in != nullptr) {
+                float s_ = 0.f, q_ = 0.f;
+                if (row_ok) {
+                  const float2* lp = p.ln_in + out_row * p.ln_slots;
+                  for (int i = 0; i < p.ln_slots; ++i) {
+                    const float2 t = __ldg(lp + i);
+                    s_ += t.x;
+                    q_ += t.y;
+                  }
+                }
+                const float mean = s_ * p.ln_inv_c;
+                const float var = fmaxf(fmaf(-mean, mean, q_ * p.ln_inv_c), 0.f);
+                ln_a = rsqrtf(var + p.ln_eps);
+                ln_b = -mean * ln_a;
+              }
+            }
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
               const int col0 = half * COLS_PER_HALF + c * 32;  // column inside the output tile
@@ -524,24 +553,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 uint32_t gt[32];
                 tmem_ld_32x32(taddr + BLOCK_N / 2 + col0, gt);
                 tmem_ld_wait();
+                if (AUX && p.ln_in != nullptr) {
+                  const float* csh = p.ln_colsum + n0;            // value rows of W'
+                  const float* csg = p.ln_colsum + p.N / 2 + n0;  // gate rows
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {  // bias tiles as 128-bit broadcast loads (2 scalar LDS per output before)
-                  const float4 bh = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
-                  const float4 bg = *reinterpret_cast<const float4*>(sbias + OUT_TILE_N + col0 + j4 * 4);
-                  v[j4 * 4 + 0] = (__uint_as_float(a[j4 * 4 + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 0]) + bg.x);
-                  v[j4 * 4 + 1] = (__uint_as_float(a[j4 * 4 + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 1]) + bg.y);
-                  v[j4 * 4 + 2] = (__uint_as_float(a[j4 * 4 + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 2]) + bg.z);
-                  v[j4 * 4 + 3] = (__uint_as_float(a[j4 * 4 + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 3]) + bg.w);
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 bh = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
+                    const float4 bg = *reinterpret_cast<const float4*>(sbias + OUT_TILE_N + col0 + j4 * 4);
+                    const float4 ch = cols_ok ? __ldg(reinterpret_cast<const float4*>(csh + j4 * 4)) : make_float4(0, 0, 0, 0);
+                    const float4 cg = cols_ok ? __ldg(reinterpret_cast<const float4*>(csg + j4 * 4)) : make_float4(0, 0, 0, 0);
+                    v[j4 * 4 + 0] = fmaf(__uint_as_float(a[j4 * 4 + 0]), ln_a, fmaf(ch.x, ln_b, bh.x)) *
+                                    gelu_erf_f(fmaf(__uint_as_float(gt[j4 * 4 + 0]), ln_a, fmaf(cg.x, ln_b, bg.x)));
+                    v[j4 * 4 + 1] = fmaf(__uint_as_float(a[j4 * 4 + 1]), ln_a, fmaf(ch.y, ln_b, bh.y)) *
+                                    gelu_erf_f(fmaf(__uint_as_float(gt[j4 * 4 + 1]), ln_a, fmaf(cg.y, ln_b, bg.y)));
+                    v[j4 * 4 + 2] = fmaf(__uint_as_float(a[j4 * 4 + 2]), ln_a, fmaf(ch.z, ln_b, bh.z)) *
+                                    gelu_erf_f(fmaf(__uint_as_float(gt[j4 * 4 + 2]), ln_a, fmaf(cg.z, ln_b, bg.z)));
+                    v[j4 * 4 + 3] = fmaf(__uint_as_float(a[j4 * 4 + 3]), ln_a, fmaf(ch.w, ln_b, bh.w)) *
+                                    gelu_erf_f(fmaf(__uint_as_float(gt[j4 * 4 + 3]), ln_a, fmaf(cg.w, ln_b, bg.w)));
+                  }
+                } else {
+#pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4) {  // bias tiles as 128-bit broadcast loads (2 scalar LDS per output before)
+                    const float4 bh = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
+                    const float4 bg = *reinterpret_cast<const float4*>(sbias + OUT_TILE_N + col0 + j4 * 4);
+                    v[j4 * 4 + 0] = (__uint_as_float(a[j4 * 4 + 0]) + bh.x) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 0]) + bg.x);
+                    v[j4 * 4 + 1] = (__uint_as_float(a[j4 * 4 + 1]) + bh.y) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 1]) + bg.y);
+                    v[j4 * 4 + 2] = (__uint_as_float(a[j4 * 4 + 2]) + bh.z) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 2]) + bg.z);
+                    v[j4 * 4 + 3] = (__uint_as_float(a[j4 * 4 + 3]) + bh.w) * gelu_erf_f(__uint_as_float(gt[j4 * 4 + 3]) + bg.w);
+                  }
                 }
               } else {
                 tmem_ld_wait();
+                if (AUX && p.ln_in != nullptr) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 bb = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
-                  v[j4 * 4 + 0] = __uint_as_float(a[j4 * 4 + 0]) + bb.x;
-                  v[j4 * 4 + 1] = __uint_as_float(a[j4 * 4 + 1]) + bb.y;
-                  v[j4 * 4 + 2] = __uint_as_float(a[j4 * 4 + 2]) + bb.z;
-                  v[j4 * 4 + 3] = __uint_as_float(a[j4 * 4 + 3]) + bb.w;
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
+                    const float4 cc = (n0 + j4 * 4 < p.n_out) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j4 * 4))
+                                                              : make_float4(0, 0, 0, 0);
+                    v[j4 * 4 + 0] = fmaf(__uint_as_float(a[j4 * 4 + 0]), ln_a, fmaf(cc.x, ln_b, bb.x));
+                    v[j4 * 4 + 1] = fmaf(__uint_as_float(a[j4 * 4 + 1]), ln_a, fmaf(cc.y, ln_b, bb.y));
+                    v[j4 * 4 + 2] = fmaf(__uint_as_float(a[j4 * 4 + 2]), ln_a, fmaf(cc.z, ln_b, bb.z));
+                    v[j4 * 4 + 3] = fmaf(__uint_as_float(a[j4 * 4 + 3]), ln_a, fmaf(cc.w, ln_b, bb.w));
+                  }
+                } else {
+#pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sbias + col0 + j4 * 4);
+                    v[j4 * 4 + 0] = __uint_as_float(a[j4 * 4 + 0]) + bb.x;
+                    v[j4 * 4 + 1] = __uint_as_float(a[j4 * 4 + 1]) + bb.y;
+                    v[j4 * 4 + 2] = __uint_as_float(a[j4 * 4 + 2]) + bb.z;
+                    v[j4 * 4 + 3] = __uint_as_float(a[j4 * 4 + 3]) + bb.w;
+                  }
                 }
               }
               const int slab = col0 >> 6;
@@ -566,6 +628,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                   } else if (p.out_scale != 1.0f) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] *= p.out_scale;
+                  }
+                  if (p.ln_out != nullptr && n0 + g * 8 < p.n_out) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      ln_s += x[j];
+                      ln_q = fmaf(x[j], x[j], ln_q);
+                    }
                   }
                   if (p.gn_partial != nullptr) {
                     float sm = 0.f, sq = 0.f;
@@ -597,6 +666,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     p.gn_partial[(static_cast<int64_t>(oct) * p.gn_blocks + blk) * 2 + (vi & 1)] = tot;
                 }
               }
+            }
+            if constexpr (AUX) {
+              if (p.ln_out != nullptr && row_ok)
+                p.ln_out[out_row * p.ln_out_slots + n_tile * 2 + half] = make_float2(ln_s, ln_q);
             }
             // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
@@ -825,7 +898,7 @@ static uav_status_t launch_instance2(IgemmParams& p, bool cluster, cudaStream_t 
 template <int BLOCK_N, bool GEGLU>
 static uav_status_t launch_instance(IgemmParams& p, bool cluster, cudaStream_t stream) {
   const bool aux = p.rowvec != nullptr || p.residual != nullptr || (p.act != UAV_ACT_NONE && p.act != UAV_ACT_GEGLU) ||
-                   p.out_scale != 1.0f || p.gn_partial != nullptr;
+                   p.out_scale != 1.0f || p.gn_partial != nullptr || p.ln_in != nullptr || p.ln_out != nullptr;
   if constexpr (IgemmCfg<BLOCK_N, GEGLU>::OUT_TILE_N >= 64) {
     if (p.tma_store) {
       return aux ? launch_instance2<BLOCK_N, GEGLU, true, true>(p, cluster, stream)
@@ -977,6 +1050,13 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   p.out_scale = e->out_scale == 0.0f ? 1.0f : e->out_scale;
   p.gn_partial = reinterpret_cast<float*>(e->gn_partial);
   p.gn_blocks = e->gn_blocks;
+  p.ln_in = reinterpret_cast<const float2*>(e->ln_in);
+  p.ln_colsum = e->ln_colsum;
+  p.ln_slots = e->ln_slots;
+  p.ln_inv_c = 1.0f / static_cast<float>(d.k_per_tap);
+  p.ln_eps = e->ln_eps;
+  p.ln_out = reinterpret_cast<float2*>(e->ln_out);
+  p.ln_out_slots = 0;
   UAV_REQUIRE(!(geglu && p.out_scale != 1.0f), "igemm: out_scale is not supported with GEGLU");
   UAV_REQUIRE(p.ld_out >= p.n_out, "igemm: ld_out (%lld) < output columns (%d)",
               (long long)p.ld_out, p.n_out);
@@ -987,6 +1067,17 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
   // TMA-store epilogue (smem-staged, fully coalesced, clips partial tiles) whenever the output
   // is an aligned fp16 tensor with at least 64-column tiles; otherwise per-row direct stores.
   p.tma_store = can_tma ? 1 : 0;
+  if (p.ln_in != nullptr || p.ln_out != nullptr) {
+    UAV_REQUIRE(can_tma && d.num_taps == 1 && d.out_strides[1] == 0,
+                "igemm: LayerNorm folding needs a Linear (single tap) with the dense fp16 TMA-store epilogue");
+    UAV_REQUIRE(p.ln_in == nullptr || (p.ln_colsum != nullptr && p.ln_slots >= 1 && p.ln_slots <= 16 &&
+                                       (reinterpret_cast<uintptr_t>(p.ln_colsum) & 15) == 0),
+                "igemm: ln_in needs ln_colsum (16-byte aligned) and 1..16 slots");
+    UAV_REQUIRE(p.ln_out == nullptr || !geglu, "igemm: ln_out is not supported with GEGLU");
+    p.ln_out_slots = (int32_t)p.n_tiles * 2;
+    UAV_REQUIRE(p.ln_out == nullptr || e->ln_out_slots == p.ln_out_slots,
+                "igemm: ln_out_slots is %d, this launch writes %d slots per row", e->ln_out_slots, p.ln_out_slots);
+  }
   if (p.gn_partial != nullptr) {
     UAV_REQUIRE(can_tma && !geglu && d.out_strides[1] == 0,
                 "igemm: GroupNorm statistics need the dense fp16 TMA-store epilogue (n_out >= 33, 16-byte aligned) without GEGLU");
@@ -1053,6 +1144,13 @@ static void pick_tile_2d(int64_t W, int64_t H, uint32_t* tw, uint32_t* th) {
 using namespace uav;
 
 extern "C" {
+
+int uav_ln_partial_slots(int64_t n_out) {
+  // two column halves per N-tile of the TMA-store epilogue (tile width 256 for N > 128, 128 for N > 64, else 64)
+  if (n_out <= 0) return 0;
+  const int tile = n_out > 128 ? 256 : (n_out > 64 ? 128 : 64);
+  return (int)((n_out + tile - 1) / tile) * 2;
+}
 
 int64_t uav_gn_partial_blocks(int64_t w, int64_t h, int64_t images) {
   if (w <= 0 || h <= 0 || images <= 0) return 0;

@@ -87,6 +87,19 @@ class Packed:
             self.cache[key] = (w, b)
         return self.cache[key]
 
+    def ln_linear(self, key: str, norm: nn.Module, mods):
+        """LayerNorm `norm` folded into the Linear layers `mods` that consume it (row-concatenated like fused_linear):
+        -> (W' = W * gamma fp16 [sum N][K], b' = b + W beta fp32, colsum fp32 [sum N] = sum_k of the fp16 W').
+        LN(x) W^T + b = rstd (x W'^T - mean colsum) + b': the GEMM epilogue applies the right-hand side (ops.linear `ln=`)."""
+        if key not in self.cache:
+            g, bta = norm.weight.detach().float(), norm.bias.detach().float()
+            w = torch.cat([m.weight.detach().float() for m in mods], dim=0)
+            b = torch.cat([(m.bias.detach().float() if m.bias is not None else
+                            torch.zeros(m.weight.shape[0], device=w.device)) for m in mods])
+            wp = (w * g[None, :]).to(torch.float16).contiguous()
+            self.cache[key] = (wp, (b + w @ bta).contiguous(), wp.float().sum(dim=1).contiguous())
+        return self.cache[key]
+
     def affine(self, m: nn.Module):
         key = id(m)
         if key not in self.cache:
@@ -431,22 +444,34 @@ class CrossAttention(nn.Module):
         self.to_v = nn.Linear(kv_dim, inner, bias=bias)
         self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
 
-    def forward(self, c: Ctx, n, hs, frames: int):
-        """n: normalised tokens (B, T, HW, C); hs: residual stream; returns to_out(attn(n)) + hs"""
-        B, T, HW, C = n.shape
+    def forward(self, c: Ctx, norm, hs, frames: int):
+        """hs: residual stream (B, T, HW, C); returns to_out(attn(LayerNorm(hs))) + hs.  The LayerNorm rides the q (or
+        q|k|v) projection's epilogue when hs carries its producer's row statistics (ops.LnStats)."""
+        B, T, HW, C = hs.shape
         if self.is_cross:
-            wq, bq = c.pk.linear(self.to_q)
-            q = ops.linear(n, wq, bq).view(B * T, HW, C)
+            q = _ln_linear(c, norm, [self.to_q], f"lnq{id(self)}", hs).view(B * T, HW, C)
             c0, cc = c.ctx_slices[id(self)]
             kv = c.ctx_kv.view(B, c.ctx_len, -1)
             k, v = kv[:, :, c0:c0 + cc], kv[:, :, c0 + cc:c0 + 2 * cc]
             o = ops.attention(q, k, v, self.heads, kv_batch_div=T)
         else:
-            w, b = c.pk.fused_linear(f"qkv{id(self)}", [self.to_q, self.to_k, self.to_v])
-            qkv = ops.linear(n, w, b).view(B * T, HW, 3 * C)
+            qkv = _ln_linear(c, norm, [self.to_q, self.to_k, self.to_v], f"lnqkv{id(self)}", hs).view(B * T, HW, 3 * C)
             o = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.heads)
         wo, bo = c.pk.linear(self.to_out[0])
-        return ops.linear(o.view(B, T, HW, C), wo, bo, residual=hs)
+        return ops.linear(o.view(B, T, HW, C), wo, bo, residual=hs, ln_stats=True)
+
+
+def _ln_linear(c: Ctx, norm: nn.LayerNorm, mods, key: str, hs, **kw):
+    """Linear(s) `mods` applied to LayerNorm(hs): folded into one GEMM when hs carries row statistics, else LayerNorm
+    kernel + GEMM on the fused weights"""
+    st = getattr(hs, "uav_ln", None)
+    if st is not None and ops.LN_FUSED and st.C == hs.shape[-1]:
+        w, b, colsum = c.pk.ln_linear(key, norm, mods)
+        return ops.linear(hs, w, b, ln=(st, colsum, norm.eps), **kw)
+    g, bt = c.pk.affine(norm)
+    n = ops.layer_norm(hs, g, bt, norm.eps)
+    w, b = c.pk.fused_linear(key + "_plain", mods) if len(mods) > 1 else c.pk.linear(mods[0])
+    return ops.linear(n, w, b, **kw)
 
 
 class RotaryEmbedding(nn.Module):
@@ -497,14 +522,13 @@ class TemporalAttention(CrossAttention):
         self.time_rel_pos_bias = RelativePositionBias(heads=heads, max_distance=32)
         self.rotary_emb = rotary_emb  # shared module: the reference state dict carries `...rotary_emb.freqs` per site
 
-    def forward(self, c: Ctx, n, hs, frames: int):
-        B, T, HW, C = n.shape
-        w, b = c.pk.fused_linear(f"qkv{id(self)}", [self.to_q, self.to_k, self.to_v])
-        qkv = ops.linear(n, w, b)
+    def forward(self, c: Ctx, norm, hs, frames: int):
+        B, T, HW, C = hs.shape
+        qkv = _ln_linear(c, norm, [self.to_q, self.to_k, self.to_v], f"lnqkv{id(self)}", hs)
         bias = c.pk.tensor(f"relbias{id(self)}_{T}", lambda: self.time_rel_pos_bias.table(T))
         o = ops.temporal_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.heads, c.rot, bias)
         wo, bo = c.pk.linear(self.to_out[0])
-        return ops.linear(o, wo, bo, residual=hs)
+        return ops.linear(o, wo, bo, residual=hs, ln_stats=True)
 
 
 class GEGLU(nn.Module):
@@ -520,9 +544,8 @@ class FeedForward(nn.Module):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
 
-    def forward(self, c: Ctx, n, hs):
-        w1, b1 = c.pk.linear(self.net[0].proj)
-        g = ops.linear(n, w1, b1, act=ops.ACT_GEGLU)
+    def forward(self, c: Ctx, norm, hs):
+        g = _ln_linear(c, norm, [self.net[0].proj], f"lnff{id(self)}", hs, act=ops.ACT_GEGLU)
         w2, b2 = c.pk.linear(self.net[2])
         return ops.linear(g, w2, b2, residual=hs)
 
@@ -554,11 +577,11 @@ class BasicTransformerBlock(nn.Module):
 
     def forward(self, c: Ctx, hs):
         T = hs.shape[1]
-        hs = self.attn1(c, self._ln(c, self.norm1, hs), hs, T)
+        hs = self.attn1(c, self.norm1, hs, T)
         if self.attn2 is not None:
-            hs = self.attn2(c, self._ln(c, self.norm2, hs), hs, T)
-        hs = self.attn_temporal(c, self._ln(c, self.norm_temporal, hs), hs, T)
-        return self.ff(c, self._ln(c, self.norm3, hs), hs)
+            hs = self.attn2(c, self.norm2, hs, T)
+        hs = self.attn_temporal(c, self.norm_temporal, hs, T)
+        return self.ff(c, self.norm3, hs)
 
 
 class Transformer3DModel(nn.Module):
@@ -585,7 +608,7 @@ class Transformer3DModel(nn.Module):
         x = self.resblock_temporal(c, x)
         hs = _gn(c, self.norm, x, False, B * T)
         w, b = c.pk.linear(self.proj_in)
-        hs = ops.linear(hs.view(B, T, H * W, C), w, b)
+        hs = ops.linear(hs.view(B, T, H * W, C), w, b, ln_stats=True)
         for blk in self.transformer_blocks:
             hs = blk(c, hs)
         w, b = c.pk.linear(self.proj_out)

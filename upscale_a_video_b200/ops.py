@@ -133,7 +133,18 @@ class GnStats:
         return 0
 
 
+class LnStats:
+    """per-row {sum, sumsq} slots of a token tensor, written by the epilogue of the Linear that produced it
+    (uav_epilogue_t.ln_out): fp32 [rows][slots][2]; attached as `tensor.uav_ln`.  The Linear that consumes
+    LayerNorm(tensor) folds the normalisation into its epilogue (uav_epilogue_t.ln_in)."""
+    __slots__ = ("partial", "slots", "C")
+
+    def __init__(self, partial, slots, C):
+        self.partial, self.slots, self.C = partial, slots, C
+
+
 GN_FUSED_STATS = __import__("os").environ.get("UAV_GN_FUSED_STATS", "1") != "0"
+LN_FUSED = __import__("os").environ.get("UAV_LN_FUSED", "1") != "0"
 
 
 def _gn_request(out: torch.Tensor, n_out: int, w: int, h: int, images: int, batch: int, e: Epilogue):
@@ -171,8 +182,11 @@ def _epi(out: torch.Tensor, bias=None, rowvec=None, rows_per_vec=0, residual=Non
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out=None,
            residual=None, rowvec=None, rows_per_vec=0, act=ACT_NONE, out_dtype=torch.float16, out_scale=1.0,
-           gn_stats=False):
-    """out[..., N] = epilogue(a[..., K] @ w[N, K]^T); a fp16 (rows may be a channel-slice view)."""
+           gn_stats=False, ln=None, ln_stats=False):
+    """out[..., N] = epilogue(a[..., K] @ w[N, K]^T); a fp16 (rows may be a channel-slice view).
+    `ln=(LnStats of a, colsum fp32 [N], eps)`: the result is LayerNorm(a) @ W^T + b with w = W * gamma, bias = b + W beta
+    pre-packed by the caller (layers.Packed.ln_linear) — the normalised tensor is never materialised.
+    `ln_stats`: emit the row statistics of the OUTPUT (`out.uav_ln`) for the LayerNorm that follows."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and w.is_contiguous()
     K = a.shape[-1]
     N = w.shape[0]
@@ -185,11 +199,22 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     e = _epi(out, bias, rowvec, rows_per_vec, residual, act, out_scale)
     st = _gn_request(out, n_out, M, 1, 1, a.shape[0] if a.dim() > 2 else 1, e) if gn_stats and act != ACT_GEGLU else None
     lib = _lib.load()
+    if ln is not None:
+        lst, colsum, eps = ln
+        assert lst.C == K and lst.partial.shape[0] == M and colsum.dtype == torch.float32 and colsum.numel() == N
+        e.ln_in, e.ln_colsum, e.ln_slots, e.ln_eps = lst.partial.data_ptr(), colsum.data_ptr(), lst.slots, eps
+    lo = None
+    if ln_stats and LN_FUSED and act != ACT_GEGLU and out.dtype == torch.float16 and n_out >= 64 and n_out % 8 == 0:
+        slots = int(lib.uav_ln_partial_slots(n_out))
+        lo = LnStats(torch.empty(M, slots, 2, dtype=torch.float32, device=out.device), slots, n_out)
+        e.ln_out, e.ln_out_slots = lo.partial.data_ptr(), slots
     with _timed("igemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out), f"linear M{M} K{K} N{N} act{act}"):
         _lib.check(lib.uav_linear(a.data_ptr(), M, K, _pixel_ld(a) if a.dim() > 1 else K, w.data_ptr(), N,
                                   out.data_ptr(), C.byref(e), _stream()), "uav_linear")
     if st is not None:
         out.uav_gn = [st]
+    if lo is not None:
+        out.uav_ln = lo
     return out
 
 
