@@ -350,10 +350,11 @@ def test_groupnorm_of_a_concat_that_is_never_built():
 
 @pytest.mark.parametrize("M,K,N,act", [(1000, 512, 512, 0), (148 * 2 * 128 + 40, 512, 1536, 0), (40000, 512, 4096, 2),
                                        (777, 1024, 1024, 0), (300, 512, 192, 0)])
-def test_layernorm_folded_into_the_consuming_linear(M, K, N, act):
+def test_layernorm_folded_into_the_consuming_linear(M, K, N, act, monkeypatch):
     """hs = Linear(...) + residual emits per-row {sum, sumsq} slots (ln_stats); the next Linear runs on the RAW hs against
     W * gamma and applies rstd (acc - mean colsum) + (b + W beta) in its epilogue == Linear(LayerNorm(hs)) of the reference
     (attention.py:525-563), without the normalised tensor ever existing"""
+    monkeypatch.setattr(ops, "LN_FUSED", True)  # opt-in path (off by default: slower at config 2, see ops.LN_FUSED)
     torch.manual_seed(7)
     a0, w0 = _rand(M, 256), _rand(K, 256, scale=0.08)
     res = _rand(M, K, scale=1.5) + 0.7          # non-zero row means: the rank-1 correction matters

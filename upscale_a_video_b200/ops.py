@@ -144,7 +144,11 @@ class LnStats:
 
 
 GN_FUSED_STATS = __import__("os").environ.get("UAV_GN_FUSED_STATS", "1") != "0"
-LN_FUSED = __import__("os").environ.get("UAV_LN_FUSED", "1") != "0"
+# LayerNorm folded into the consuming Linear (uav_epilogue_t.ln_in / ln_out).  OFF by default: measured on B200 at config 2
+# the UNet forward got 24 ms SLOWER with it (LayerNorm kernels -8.9 ms, but +33 ms in the short-K Linears whose epilogue
+# is their critical path: they leave the lean bias-only instance for the 168-register AUX one, + row-statistics loads,
+# + column-sum loads, + 2 FMA per element on the producers).  Kept as an opt-in (UAV_LN_FUSED=1) with its parity test.
+LN_FUSED = __import__("os").environ.get("UAV_LN_FUSED", "0") == "1"
 
 
 def _gn_request(out: torch.Tensor, n_out: int, w: int, h: int, images: int, batch: int, e: Epilogue):
