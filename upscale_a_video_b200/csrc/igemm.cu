@@ -111,6 +111,7 @@ struct alignas(64) IgemmParams {
   // main loop and costs no shared memory); 2 = loaded ONE TILE AHEAD into a dedicated buffer carved from the end of the
   // ring (single-tap GEMMs: HBM / epilogue bound, an exposed load latency per tile would be the critical path)
   int32_t res_mode;
+  int32_t staging_tiles;  // 1, or 2 (GEGLU): output tiles alternate between two staging buffers
   const float* bias;
   const __half* rowvec;
   int64_t rows_per_vec, ld_rowvec;
@@ -137,7 +138,11 @@ struct IgemmCfg {
   static constexpr int OUT_TILE_N = GEGLU ? BLOCK_N / 2 : BLOCK_N;
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGING_BYTES = (OUT_TILE_N >= 64) ? (OUT_TILE_N / 64) * SLAB_BYTES : 0;
+  static constexpr int TILE_STAGING_BYTES = (OUT_TILE_N >= 64) ? (OUT_TILE_N / 64) * SLAB_BYTES : 0;
+  // GEGLU tiles are 128 output columns (32 KB): two staging tiles, so the TMA store of tile i drains while the epilogue of
+  // tile i + 1 fills the other one (with a single tile every epilogue starts by waiting for the previous store)
+  static constexpr int STAGING_TILES = GEGLU ? 2 : 1;
+  static constexpr int STAGING_BYTES = TILE_STAGING_BYTES * STAGING_TILES;
   static constexpr int AUX_BYTES = 2048;  // barriers + tmem slot + bias tile (256 floats)
   // everything left of the 227 KB after the output staging tile is one region shared by the A and B rings
   static constexpr int RING_BYTES = ((232448 - 1024 - STAGING_BYTES - AUX_BYTES) / 1024) * 1024;
@@ -241,8 +246,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + SA * A_STAGE_BYTES;
   constexpr int B_STAGE = Cfg::B_STAGE_BYTES / CL;  // bytes of one weight stage in THIS CTA
-  uint8_t* staging = smem + Cfg::RING_BYTES;
-  uint8_t* aux = staging + Cfg::STAGING_BYTES;
+  uint8_t* staging0 = smem + Cfg::RING_BYTES;
+  uint8_t* aux = staging0 + Cfg::STAGING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
   constexpr int MAXS = 10;
   uint64_t* fulla_bar = bars;                     // [MAXS]
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* res_bar = bars + 4 * MAXS + 5;        // [1] residual tile landed in shared memory
   float* sbias = reinterpret_cast<float*>(aux + 512);  // [BLOCK_N]
   // residual tile: the staging tile itself (mode 1) or the last STAGING_BYTES of the ring region (mode 2)
-  uint8_t* res_smem = (p.res_mode == 2) ? (smem + Cfg::RING_BYTES - Cfg::STAGING_BYTES) : staging;
+  uint8_t* res_tile_ahead = smem + Cfg::RING_BYTES - Cfg::TILE_STAGING_BYTES;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t l4 = r;
     uint32_t res_phase = 0;
     // one thread: TMA-load the residual tile (64-column slabs, the layout the epilogue stores) and arm res_bar
-    auto issue_res_load = [&](int nb, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4) {
+    auto issue_res_load = [&](uint8_t* res_smem, int nb, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4) {
       uint32_t bytes = 0;
 #pragma unroll
       for (int sl = 0; sl < (OUT_TILE_N >= 64 ? OUT_TILE_N / 64 : 0); ++sl)
@@ -483,6 +488,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
         if constexpr (TMA_EPI) {
           {
+            uint8_t* staging = staging0 + (p.staging_tiles == 2 ? (it & 1) * Cfg::TILE_STAGING_BYTES : 0);
+            uint8_t* res_smem = (p.res_mode == 2) ? res_tile_ahead : staging;
             // ---- stage the bias tile, make sure the previous TMA store released the staging ----
             if (GEGLU) {
               const int j = et & (OUT_TILE_N - 1);
@@ -494,11 +501,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             }
             constexpr int COLS_PER_HALF = OUT_TILE_N / 2;
             constexpr int CHUNKS = COLS_PER_HALF / 32;
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (et == 0) {  // the store that last used THIS staging tile must have read it
+              if (p.staging_tiles == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
             if constexpr (AUX) {
               // mode 1: the staging tile is free now -> fetch this tile's residual into it (in-place epilogue); the first
               // tile of mode 2 is fetched here too (later ones are issued one tile ahead, right after the store below)
-              if (et == 0 && (p.res_mode == 1 || (p.res_mode == 2 && it == 0))) issue_res_load(n_base, t1, t2, t3, t4);
+              if (et == 0 && (p.res_mode == 1 || (p.res_mode == 2 && it == 0))) issue_res_load(res_smem, n_base, t1, t2, t3, t4);
             }
             epi_bar_sync();
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -706,7 +716,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                   i2 /= p.tiles[2];
                   const uint32_t u3 = (i2 % p.tiles[3]) * p.box[3];
                   i2 /= p.tiles[3];
-                  issue_res_load((wn % p.n_tiles) * OUT_TILE_N, u1, u2, u3, i2 * p.box[4]);
+                  issue_res_load(res_tile_ahead, (wn % p.n_tiles) * OUT_TILE_N, u1, u2, u3, i2 * p.box[4]);
                 }
               }
             }
@@ -1013,8 +1023,10 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
     // (9 taps) -> balanced rings.  Single-tap GEMMs stream activations from HBM (high latency) against L2-resident
     // weights -> deep A ring, shallow B ring.
     const int b_stage = block_n * BLOCK_K * 2 / (use_cluster ? 2 : 1);  // CTA pairs hold half a weight tile each
-    const int staging = out_tile_n >= 64 ? (out_tile_n / 64) * SLAB_BYTES : 0;
-    int ring = ((232448 - 1024 - staging - 2048) / 1024) * 1024;  // == IgemmCfg::RING_BYTES
+    const int staging = out_tile_n >= 64 ? (out_tile_n / 64) * SLAB_BYTES : 0;  // one output tile
+    static const bool double_staging = !(getenv("UAV_IGEMM_DOUBLE_STAGING") && getenv("UAV_IGEMM_DOUBLE_STAGING")[0] == '0');
+    p.staging_tiles = (geglu && double_staging) ? 2 : 1;
+    int ring = ((232448 - 1024 - staging * (geglu ? 2 : 1) - 2048) / 1024) * 1024;  // == IgemmCfg::RING_BYTES
     p.res_mode = 0;
     if (can_tma && e->residual != nullptr) {
       static const int res_knob = getenv("UAV_IGEMM_RES_MODE") ? atoi(getenv("UAV_IGEMM_RES_MODE")) : -1;
