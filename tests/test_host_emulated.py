@@ -38,12 +38,17 @@ def unet_sd():
     return make_state_dict(shapes, meta["seed_unet"])
 
 
+_MODELS = {}  # one instance per model for the whole module: building the 691 M-parameter UNet costs more than most tests
+
+
 def _unet(unet_sd):
-    from upscale_a_video_b200.unet_video import UNetVideoModel
-    cfg = json.load(open(os.path.join(CFG, "unet_video_config.json")))
-    m = UNetVideoModel.from_config(cfg)
-    m.load_state_dict(unet_sd, strict=True)
-    return m.half().eval()
+    if "unet" not in _MODELS:
+        from upscale_a_video_b200.unet_video import UNetVideoModel
+        cfg = json.load(open(os.path.join(CFG, "unet_video_config.json")))
+        m = UNetVideoModel.from_config(cfg)
+        m.load_state_dict(unet_sd, strict=True)
+        _MODELS["unet"] = m.half().eval()
+    return _MODELS["unet"]
 
 
 @pytest.mark.parametrize("case", ["t3_16x24", "t2_20x28_upsize"])
@@ -64,6 +69,16 @@ def test_unet_host_logic_vs_golden(emulated, unet_sd, case):
     assert not torch.equal(out, out3)
 
 
+def test_unet_host_logic_layernorm_folded(emulated, unet_sd, monkeypatch):
+    """opt-in path (UAV_LN_FUSED=1): every LayerNorm of the transformer blocks folded into the Linear that consumes it
+    (gamma-scaled weights, column sums, rank-1 correction) — same golden, same band"""
+    monkeypatch.setattr(emu_ops, "LN_FUSED", True)
+    c = torch.load(os.path.join(G, "unet.pt"), weights_only=False)["t8_8x8"]
+    out = _unet(unet_sd)(c["sample"].half(), torch.tensor(c["timestep"]), c["low_res"].half(),
+                         encoder_hidden_states=c["ctx"].half(), class_labels=c["class_labels"]).sample
+    assert _rel(out, c["out"]) < 5e-3
+
+
 def test_unet_shared_cfg_prefix_host_logic(emulated, unet_sd):
     m = _unet(unet_sd)
     c = torch.load(os.path.join(G, "unet.pt"), weights_only=False)["t3_16x24"]
@@ -78,13 +93,15 @@ def test_unet_shared_cfg_prefix_host_logic(emulated, unet_sd):
 
 
 def _vae(kind):
-    from oracle.weights import make_state_dict
-    from upscale_a_video_b200 import AutoencoderKLVideo
-    meta = json.load(open(os.path.join(G, "meta.json")))
-    shapes = json.load(open(os.path.join(G, f"shapes_{kind}.json")))
-    m = AutoencoderKLVideo.from_config(json.load(open(os.path.join(CFG, f"{kind}_config.json"))))
-    m.load_state_dict(make_state_dict(shapes, meta["seed_vae"]), strict=True)
-    return m.eval()
+    if kind not in _MODELS:
+        from oracle.weights import make_state_dict
+        from upscale_a_video_b200 import AutoencoderKLVideo
+        meta = json.load(open(os.path.join(G, "meta.json")))
+        shapes = json.load(open(os.path.join(G, f"shapes_{kind}.json")))
+        m = AutoencoderKLVideo.from_config(json.load(open(os.path.join(CFG, f"{kind}_config.json"))))
+        m.load_state_dict(make_state_dict(shapes, meta["seed_vae"]), strict=True)
+        _MODELS[kind] = m.eval()
+    return _MODELS[kind]
 
 
 def test_vae_host_logic_vs_golden(emulated):
@@ -254,8 +271,8 @@ image, fw, bw, pe = bench.synth_inputs(T, H, W, "cpu")
 g = torch.Generator().manual_seed(5)
 noise, lat0 = torch.randn(1, 3, T, H, W, generator=g), torch.randn(1, 4, T, H, W, generator=g)
 neg, pos = pe.half().chunk(2)
-kw = dict(image=image, flows_bi=[fw, bw], num_inference_steps=2, guidance_scale=6.0, noise_level=120, prompt_embeds=pos,
-          negative_prompt_embeds=neg, latents=lat0, noise=noise, propagation_steps=[1], return_dict=False)
+kw = dict(image=image, flows_bi=[fw, bw], num_inference_steps=1, guidance_scale=6.0, noise_level=120, prompt_embeds=pos,
+          negative_prompt_embeds=neg, latents=lat0, noise=noise, propagation_steps=[0], return_dict=False)
 calls = {"n": 0}
 orig_forward = unet.forward
 def counting(*a, **k):
@@ -268,25 +285,41 @@ n_solo = calls["n"]
 calls["n"] = 0
 pipe.process_group = None
 out2, lat2 = pipe(None, **kw)
-assert n_solo == 4 and calls["n"] == 2, (n_solo, calls["n"])  # 2 windows x 2 steps alone, 1 window x 2 steps when sharded
+assert n_solo == 2 and calls["n"] == 1, (n_solo, calls["n"])  # 2 windows alone, 1 window per rank when sharded
 assert torch.equal(lat1, lat2) and torch.equal(out1, out2), ((lat1 - lat2).abs().max(), (out1 - out2).abs().max())
-# 20 frames = 3 unique windows on 2 ranks: dealt as 6 CFG-half units (3 half-calls per rank instead of 2 full rounds)
+# 20 frames = 3 unique windows on 2 ranks: dealt as 6 CFG-half units (3 single-half calls per rank instead of 2 rounds of whole
+# windows).  The dealing / gather / blend-order logic does not depend on what the UNet computes, so this part runs a tiny
+# stand-in UNet and decoder (per-batch-item deterministic functions): sharded == unsharded bit for bit.
 from upscale_a_video_b200 import sharding
 assert sharding.window_units(3, 2, True) == [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)]
+from types import SimpleNamespace
+class TinyUNet:
+    config = SimpleNamespace(in_channels=7)
+    calls = 0
+    def forward(self, sample, timestep, low_res, encoder_hidden_states=None, class_labels=None, cfg_shared_input=False):
+        TinyUNet.calls += 1
+        m = encoder_hidden_states.float().mean(dim=(1, 2)).view(-1, 1, 1, 1, 1)
+        y = torch.tanh(sample.float() * 0.7 + low_res.float().mean(1, keepdim=True) * 0.3 + m + 0.001 * float(timestep))
+        return SimpleNamespace(sample=y.to(sample.dtype))
+    __call__ = forward
+class TinyVAE:
+    config = SimpleNamespace(latent_channels=4, out_channels=3, scaling_factor=0.08333)
+    def decode(self, z, img=None, w_lr=1, latent_scale=1.0, clamp=False):
+        up = (z.float() * latent_scale)[:, :3].repeat_interleave(4, dim=-2).repeat_interleave(4, dim=-1)
+        return SimpleNamespace(sample=up.clamp(-1, 1) if clamp else up)
+tiny = VideoUpscalePipeline(None, None, DDPMScheduler(beta_schedule="scaled_linear"),
+                            DDIMScheduler(**meta["sched_cfgs"]["v_scaled_offset"]), TinyVAE(), TinyUNet(), Propagation(4, learnable=False))
 T = 20
 image, fw, bw, pe = bench.synth_inputs(T, H, W, "cpu")
 noise, lat0 = torch.randn(1, 3, T, H, W, generator=g), torch.randn(1, 4, T, H, W, generator=g)
-kw.update(image=image, flows_bi=[fw, bw], latents=lat0, noise=noise, num_inference_steps=1, propagation_steps=[0])
-calls["n"] = 0
-pipe.process_group = solo
-out1, lat1 = pipe(None, **kw)
-n_solo = calls["n"]
-calls["n"] = 0
-pipe.process_group = None
-out2, lat2 = pipe(None, **kw)
-assert n_solo == 3 and calls["n"] == 3, (n_solo, calls["n"])  # 3 windows alone; 3 single-half calls per rank when sharded
-rel = ((lat1.float() - lat2.float()).norm() / lat1.float().norm()).item()
-assert rel < 2e-3, rel  # batch-1 and batch-2 calls may pick different CPU conv algorithms: not bit-identical
+kw.update(image=image, flows_bi=[fw, bw], latents=lat0, noise=noise, num_inference_steps=2, propagation_steps=[1])
+tiny.process_group = solo
+out1, lat1 = tiny(None, **kw)
+n_solo, TinyUNet.calls = TinyUNet.calls, 0
+tiny.process_group = None
+out2, lat2 = tiny(None, **kw)
+assert n_solo == 6 and TinyUNet.calls == 6, (n_solo, TinyUNet.calls)  # 3 windows x 2 steps alone; 3 half-calls x 2 steps per rank
+assert torch.equal(lat1, lat2) and torch.equal(out1, out2)
 dist.barrier()
 if rank == 0:
     print("SHARDED_PIPELINE_OK")
