@@ -9,10 +9,11 @@ from upscale_a_video_b200 import ops
 dev = torch.device("cuda")
 pipe = bench.build_pipeline(dev)
 T = 8
-image, fw, bw, pe = bench.synth_inputs(T, bench.H_LR, bench.W_LR, dev)
+C2 = bench.CONFIGS["c2"]
+image, fw, bw, pe = bench.synth_inputs(T, C2["h"], C2["w"], dev)
 neg, pos = pe.half().to(dev).chunk(2)
-kw = dict(num_inference_steps=bench.STEPS_DDIM, guidance_scale=bench.GUIDANCE, noise_level=bench.NOISE_LEVEL,
-          propagation_steps=list(bench.PROP_STEPS), prompt_embeds=pos, negative_prompt_embeds=neg)
+kw = dict(num_inference_steps=C2["steps"], guidance_scale=bench.GUIDANCE, noise_level=bench.NOISE_LEVEL,
+          propagation_steps=list(C2["prop"]), prompt_embeds=pos, negative_prompt_embeds=neg)
 
 
 def run():
