@@ -1030,8 +1030,10 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
     p.res_mode = 0;
     if (can_tma && e->residual != nullptr) {
       static const int res_knob = getenv("UAV_IGEMM_RES_MODE") ? atoi(getenv("UAV_IGEMM_RES_MODE")) : -1;
-      // single-tap GEMMs are HBM / epilogue bound: residual one tile ahead in its own buffer (if >= 3 stages remain)
-      const bool ahead = d.num_taps == 1 && (ring - staging) / (A_STAGE_BYTES + b_stage) >= 3;
+      // short-K single-tap GEMMs are HBM / epilogue bound: residual one tile ahead in its own buffer (if >= 3 stages
+      // remain).  With K >= 1024 the ring stage it costs is worth more than the early residual (tools/bench_linear512.py,
+      // B200: K=2048 N=512 1443 -> 1322 us, K=1024 N=1024 117 -> 108 us in mode 1; K=512 541 vs 548 us, M=184320 167 vs 184)
+      const bool ahead = d.num_taps == 1 && d.k_per_tap <= 512 && (ring - staging) / (A_STAGE_BYTES + b_stage) >= 3;
       p.res_mode = res_knob > 0 ? res_knob : (ahead ? 2 : 1);
       if (p.res_mode == 2 && (ring - staging) / (A_STAGE_BYTES + b_stage) < 2) p.res_mode = 1;
       if (p.res_mode == 2) ring -= staging;
