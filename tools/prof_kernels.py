@@ -21,6 +21,10 @@ elif which == "linear_res":  # attention to_out / proj_out: Linear 512->512 + re
     a, w, b, r = rnd(2, 8, 46080, 512), rnd(512, 512, scale=0.02), torch.zeros(512, device=dev), rnd(2, 8, 46080, 512)
     out = torch.empty_like(r)
     f = lambda: ops.linear(a, w, b, residual=r, out=out)
+elif which == "linear_plain":  # attention to_q / text-attention to_q: Linear 512->512, no residual, M = 737 280
+    a, w, b = rnd(2, 8, 46080, 512), rnd(512, 512, scale=0.02), torch.zeros(512, device=dev)
+    out = torch.empty(2, 8, 46080, 512, device=dev, dtype=torch.float16)
+    f = lambda: ops.linear(a, w, b, out=out)
 elif which == "linear_res_gn":
     a, w, b, r = rnd(2, 8, 46080, 512), rnd(512, 512, scale=0.02), torch.zeros(512, device=dev), rnd(2, 8, 46080, 512)
     out = torch.empty_like(r)
