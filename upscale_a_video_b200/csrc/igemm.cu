@@ -1041,10 +1041,12 @@ static uav_status_t launch_igemm(const IgemmDesc& d, cudaStream_t stream) {
     int sb = ring / (A_STAGE_BYTES + b_stage);  // balanced depth
     if (sb > 10) sb = 10;
     int sa = sb;
-    // measured on B200: no gain (the weight ring becomes the limiter) -> opt-in only
-    static const bool deep_a = getenv("UAV_IGEMM_DEEP_A") && getenv("UAV_IGEMM_DEEP_A")[0] == '1';
-    if (deep_a && d.num_taps == 1 && sb > 2) {
-      sb = 2;
+    // single-tap GEMMs: a shallower weight ring (L2 hits) buys activation stages (HBM latency).  UAV_IGEMM_B_STAGES=n
+    // sets the weight depth; UAV_IGEMM_DEEP_A=1 is n = 2 (measured on B200: the weight ring becomes the limiter)
+    static const int b_knob = getenv("UAV_IGEMM_B_STAGES") ? atoi(getenv("UAV_IGEMM_B_STAGES"))
+                              : ((getenv("UAV_IGEMM_DEEP_A") && getenv("UAV_IGEMM_DEEP_A")[0] == '1') ? 2 : 0);
+    if (b_knob >= 2 && d.num_taps == 1 && sb > b_knob) {
+      sb = b_knob;
       sa = (ring - sb * b_stage) / A_STAGE_BYTES;
       if (sa > 10) sa = 10;
     }
